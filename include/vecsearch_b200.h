@@ -1,0 +1,159 @@
+/* vecsearch_b200.h -- C ABI of the B200-native exact cosine vector-search engine.
+ *
+ * This is the drop-in boundary for the reference's vector-store seam.  The reference
+ * (parsakhaz/multimodal-image-similarity-search) has no FFI layer of its own: the seam is the
+ * duck-typed chromadb Collection returned by init_chromadb() (backend/app/utils.py:104-138)
+ * and used as the module global `collection` (backend/app/main.py:77,530).  Each entry point
+ * below names the Collection call (reference file:line) whose arithmetic it replaces; the
+ * Python class that re-creates the Collection surface on top of these symbols lives in
+ * multimodal-image-similarity-search_b200/collection.py and INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, int status return (0 = ok, <0 = error, text via
+ *    vs_last_error()); no exceptions, no torch types, no hidden allocation on the query path
+ *    beyond per-index scratch that is grown once and reused.
+ *  - one vs_index_t == one row shard resident in the HBM of ONE device.  Multi-GPU = one
+ *    process per GPU, each owning a shard; candidates are exchanged by the host layer
+ *    (NCCL all-gather) and merged with vs_merge_topk_dev.
+ *  - "_host" entry points take HOST buffers and include the H2D/D2H copies and the final
+ *    stream synchronise; "_dev" entry points take DEVICE buffers and are asynchronous on the
+ *    given cudaStream_t (passed as void*; NULL = the index's own stream).
+ *  - scores are float32 cosine similarities (distance = 1 - score); rows are int64 shard-local
+ *    row numbers plus the index's row_base; ranking is (score desc, row asc); empty result
+ *    slots (k > count) carry score = -inf and row = -1.
+ *  - there is NO CPU fallback: every compute entry point fails with VS_ERR_CUDA when no
+ *    sm_100 device is usable.
+ */
+#ifndef VECSEARCH_B200_H
+#define VECSEARCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vs_index vs_index_t;
+
+enum { VS_F32 = 0, VS_BF16 = 1 };
+
+enum {
+  VS_OK = 0,
+  VS_ERR_ARG = -1,    /* bad argument */
+  VS_ERR_CUDA = -2,   /* CUDA runtime / driver error, or no usable device */
+  VS_ERR_OOM = -3,    /* device allocation failed */
+  VS_ERR_UNSUPPORTED = -4,
+  VS_ERR_OVERFLOW = -5 /* caller-provided output buffer too small (dedup pairs) */
+};
+
+/* number of filter bits carried per row (4 x u64) -- the reference UI never has more than a
+ * handful of filters (filters.json); 256 matches BASELINE config 4. */
+#define VS_MASK_WORDS 4
+
+/* Thread-local text of the last error raised on the calling thread. */
+const char* vs_last_error(void);
+
+/* ABI version of this header (bumped on any signature change). */
+int vs_abi_version(void);
+
+/* ---- lifecycle: replaces chromadb.PersistentClient(...).create_collection(name,
+ *      metadata={"hnsw:space":"cosine"})  (backend/app/utils.py:113-130).  Only the cosine
+ *      space exists.  `capacity_rows` is a reservation hint; the slab grows by doubling. */
+int vs_create(int device, int dim, int dtype, int64_t capacity_rows, vs_index_t** out);
+int vs_destroy(vs_index_t* ix);
+
+/* Collection.count()  (init_db.py:58). */
+int64_t vs_count(const vs_index_t* ix);
+int vs_dim(const vs_index_t* ix);
+int vs_dtype(const vs_index_t* ix);
+
+/* Offset added to every row number this shard reports (global row = row_base + local row). */
+int vs_set_row_base(vs_index_t* ix, int64_t row_base);
+
+/* ---- ingest: Collection.add(ids, embeddings, ...)  (backend/app/main.py:735-740).
+ *      Appends n float32 rows [n, dim] (row-major, contiguous); the kernel casts to the storage
+ *      dtype and stores 1/(||row||+1e-30) of the STORED row beside it.  *first_row receives the
+ *      local row number of the first appended row.  id<->row bookkeeping is the host layer's. */
+int vs_add_host(vs_index_t* ix, const float* rows, int64_t n, int64_t* first_row);
+int vs_add_dev(vs_index_t* ix, const float* rows_dev, int64_t n, int64_t* first_row, void* stream);
+
+/* ---- Collection.delete(ids)  (backend/app/main.py:1069).  Removes local row `row` by moving
+ *      the LAST row into its place (dense slab, no tombstones).  *moved_from = the row that was
+ *      moved (== old count-1), or -1 if `row` was the last row. */
+int vs_remove(vs_index_t* ix, int64_t row, int64_t* moved_from);
+
+/* Drop all rows, keep the allocation  (reset path, backend/app/main.py:1058-1098). */
+int vs_clear(vs_index_t* ix);
+
+/* ---- per-row filter bits: bit f set <=> stored answer for filter f is "yes"
+ *      (the predicate of backend/app/main.py:215, written by :1010-1033). */
+int vs_set_mask_bits(vs_index_t* ix, int64_t row, const uint64_t bits[VS_MASK_WORDS]);
+int vs_get_mask_bits(const vs_index_t* ix, int64_t row, uint64_t bits[VS_MASK_WORDS]);
+
+/* Copy stored rows back as float32 (Collection.get(include=["embeddings"]) and persistence). */
+int vs_get_rows_host(const vs_index_t* ix, int64_t first_row, int64_t n, float* out);
+
+/* ---- query: Collection.query(query_embeddings=[...], n_results=k, ...)
+ *      (backend/app/main.py:761-765; legacy app.py:310-314).
+ *      q: [B, dim] float32, NOT assumed unit-norm (normalised on device).
+ *      require_bits: NULL, or VS_MASK_WORDS words applied to every query: only rows whose
+ *      filter bits contain all required bits compete ("pre" filter mode, fused in the scan).
+ *      mode: VS_Q_AUTO picks the HBM-bound scan (B small, or f32 storage) or the tcgen05
+ *      batched kernel (bf16 storage, B >= 16); the other values force one path.
+ *      out_scores/out_rows: [B, k].  k <= 1024 (main.py:757 caps "All" at 1000). */
+enum { VS_Q_AUTO = 0, VS_Q_SCAN = 1, VS_Q_TENSOR = 2 };
+int vs_query_topk_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits,
+                       int mode, float* out_scores, int64_t* out_rows);
+int vs_query_topk_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits,
+                      int mode, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+
+/* ---- multimodal blend: search_multimodal  (backend/app/main.py:850-860):
+ *      c = w*img/||img|| + (1-w)*txt/||txt||, c /= ||c||, for B (img, txt, w) triples -> [B, dim]
+ *      float32 on the device; feed the result to vs_query_topk_dev.  Weights are float64 (the
+ *      reference's python float): w and 1-w are each rounded to float32 once, as numpy does. */
+int vs_blend_dev(vs_index_t* ix, const float* img_dev, const float* txt_dev, const double* w_dev,
+                 int B, float* out_dev, void* stream);
+/* search_multimodal end to end with HOST buffers: H2D of both embeddings and the weights, blend
+ * kernel, query, D2H (the body of backend/app/main.py:829-867 after the two CLIP calls). */
+int vs_query_multimodal_host(vs_index_t* ix, const float* img, const float* txt, const double* w, int B,
+                             int k, const uint64_t* require_bits, int mode, float* out_scores,
+                             int64_t* out_rows);
+
+/* ---- k-way merge of per-shard candidates after the all-gather:
+ *      cand_scores/cand_rows: [G, B, k] device buffers (rows are global, <0 = empty) ->
+ *      out [B, k].  `device` selects the GPU when ix is NULL. */
+int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev,
+                      int G, int B, int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+
+/* ---- filter sweep (BASELINE config 4; CLIP-side analogue of process_filter_on_all_images,
+ *      backend/app/main.py:939-1056): prompts [F, dim] float32 (host or device) -> bit mask
+ *      out_bits[F][words_per_filter] (uint32, bit n%32 of word n/32 set <=> cos >= tau),
+ *      words_per_filter = ceil(count/32) rounded up to a multiple of 4.  tcgen05, bf16 storage. */
+int64_t vs_filter_words(const vs_index_t* ix);
+int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float tau,
+                        uint32_t* out_bits_dev, void* stream);
+int vs_filter_sweep_host(vs_index_t* ix, const float* prompts, int F, float tau, uint32_t* out_bits);
+
+/* ---- all-pairs duplicate detection (BASELINE config 5; embedding analogue of the pHash id
+ *      lookup, backend/app/main.py:627-640): pairs (i<j) with cos >= tau among the rows
+ *      [row_lo, row_hi) x [0, count) of this index (row ranges let G ranks split the triangle).
+ *      Pairs are appended unordered to out_i/out_j/out_score (device, capacity `cap`);
+ *      *out_count_dev receives the number found (may exceed cap -> VS_ERR_OVERFLOW from the
+ *      host variant; the device variant just stops writing). */
+int vs_dedup_dev(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int64_t cap,
+                 int64_t* out_i_dev, int64_t* out_j_dev, float* out_score_dev,
+                 unsigned long long* out_count_dev, void* stream);
+int vs_dedup_host(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int64_t cap,
+                  int64_t* out_i, int64_t* out_j, float* out_score, int64_t* out_count);
+
+/* ---- introspection for bench.py / tests: number of kernels this library has launched on the
+ *      calling process since load (the "gpu_launches" claim), and the last query's path. */
+uint64_t vs_launch_count(void);
+int vs_last_query_path(const vs_index_t* ix);   /* VS_Q_SCAN or VS_Q_TENSOR */
+int vs_device_sm_count(const vs_index_t* ix);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECSEARCH_B200_H */

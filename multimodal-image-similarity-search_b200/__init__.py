@@ -1,0 +1,15 @@
+"""B200-native exact cosine vector search: drop-in for the chromadb collection of
+parsakhaz/multimodal-image-similarity-search (import name: ``mmiss_b200``).
+
+The directory is called ``multimodal-image-similarity-search_b200`` (not a valid Python
+identifier); ``mmiss_b200.py`` at the repo root loads it under the importable name.
+"""
+from ._native import VecSearchError, LIB_PATH, launch_count, load as load_native  # noqa: F401
+from .index import DeviceIndex  # noqa: F401
+from .collection import Collection, PersistentClient, Client  # noqa: F401
+from .service import SearchService, apply_filters, similarity_from_distance  # noqa: F401
+from .sharded import ShardedSearcher, shard_bounds  # noqa: F401
+
+__all__ = ["VecSearchError", "DeviceIndex", "Collection", "PersistentClient", "Client", "SearchService",
+           "apply_filters", "similarity_from_distance", "ShardedSearcher", "shard_bounds", "launch_count",
+           "load_native", "LIB_PATH"]

@@ -1,0 +1,690 @@
+// api.cu -- the C ABI declared in include/vecsearch_b200.h: index handle, slab management,
+// host<->device staging, path selection.  No compute happens on the host.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/vecsearch_b200.h"
+#include "kernels.h"
+
+namespace vs {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+}  // namespace vs
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      cudaGetLastError();                                                                          \
+      return fail(e__ == cudaErrorMemoryAllocation ? VS_ERR_OOM : VS_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                    \
+    }                                                                                              \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    bytes = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return e;
+    bytes = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct vs_index {
+  int device = 0;
+  int dim = 0;
+  int dtype = 0;
+  int esize = 4;
+  int64_t ld = 0;        // row pitch in elements
+  int64_t n = 0;
+  int64_t cap = 0;
+  int64_t row_base = 0;
+  int sm_count = 148;
+  int last_path = 0;
+  void* rows = nullptr;
+  float* inv = nullptr;
+  uint64_t* mask = nullptr;   // lazily allocated [cap][4]
+  bool any_mask = false;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  // scratch
+  DevBuf d_q, d_out_s, d_out_r, d_part_s, d_part_r, d_tickets, d_scores, d_select, d_tensor, d_stage, d_misc;
+  HostBuf h_in, h_out;
+  size_t tickets_n = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+    if (!ok) cudaGetLastError();
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int64_t pitch_elems(int dim, int esize) {
+  const int per16 = 16 / esize;
+  return ((int64_t)dim + per16 - 1) / per16 * per16;
+}
+
+int grow(vs_index* ix, int64_t need_rows) {
+  if (need_rows <= ix->cap) return VS_OK;
+  int64_t ncap = ix->cap > 0 ? ix->cap : 1024;
+  while (ncap < need_rows) ncap += ncap < (1 << 20) ? ncap : ncap / 2;
+  const size_t row_bytes = (size_t)ix->ld * ix->esize;
+  void* nrows = nullptr;
+  float* ninv = nullptr;
+  // +64 floats: the scan's bulk copy of inverse norms rounds the tail up to 4 entries
+  cudaError_t e = cudaMalloc(&nrows, (size_t)ncap * row_bytes + 256);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(VS_ERR_OOM, "cudaMalloc(%zu) for %lld rows failed: %s", (size_t)ncap * row_bytes, (long long)ncap,
+                cudaGetErrorString(e));
+  }
+  e = cudaMalloc((void**)&ninv, ((size_t)ncap + 64) * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(nrows);
+    return fail(VS_ERR_OOM, "cudaMalloc inverse norms failed: %s", cudaGetErrorString(e));
+  }
+  CU(cudaMemsetAsync(ninv, 0, ((size_t)ncap + 64) * sizeof(float), ix->stream));
+  uint64_t* nmask = nullptr;
+  if (ix->mask) {
+    e = cudaMalloc((void**)&nmask, (size_t)ncap * vs::kMaskWords * 8);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(nrows);
+      cudaFree(ninv);
+      return fail(VS_ERR_OOM, "cudaMalloc filter bits failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemsetAsync(nmask, 0, (size_t)ncap * vs::kMaskWords * 8, ix->stream));
+  }
+  if (ix->n > 0) {
+    CU(cudaMemcpyAsync(nrows, ix->rows, (size_t)ix->n * row_bytes, cudaMemcpyDeviceToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ninv, ix->inv, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    if (nmask)
+      CU(cudaMemcpyAsync(nmask, ix->mask, (size_t)ix->n * vs::kMaskWords * 8, cudaMemcpyDeviceToDevice, ix->stream));
+  }
+  // rare path: wait for everything (adds/queries may be in flight on caller streams)
+  CU(cudaDeviceSynchronize());
+  if (ix->rows) cudaFree(ix->rows);
+  if (ix->inv) cudaFree(ix->inv);
+  if (ix->mask) cudaFree(ix->mask);
+  ix->rows = nrows;
+  ix->inv = ninv;
+  ix->mask = nmask;
+  ix->cap = ncap;
+  return VS_OK;
+}
+
+int ensure_mask(vs_index* ix) {
+  if (ix->mask) return VS_OK;
+  if (ix->cap == 0) {
+    int rc = grow(ix, 1);
+    if (rc) return rc;
+  }
+  CU(cudaMalloc((void**)&ix->mask, (size_t)ix->cap * vs::kMaskWords * 8));
+  CU(cudaMemsetAsync(ix->mask, 0, (size_t)ix->cap * vs::kMaskWords * 8, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
+cudaStream_t pick_stream(vs_index* ix, void* stream) { return stream ? (cudaStream_t)stream : ix->stream; }
+
+// queries per scan launch (bounds the partial-list workspace)
+constexpr int kScanBatch = 64;
+
+int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint64_t* req, int mode, float* out_s,
+                     int64_t* out_r, cudaStream_t st) {
+  if (B <= 0) return VS_OK;
+  if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
+  if (ix->n == 0) {
+    // empty collection: all slots empty
+    CU(vs::launch_fill_empty(out_s, out_r, (int64_t)B * k, st));
+    return VS_OK;
+  }
+  bool use_mask = false;
+  uint64_t reqw[vs::kMaskWords] = {0, 0, 0, 0};
+  if (req)
+    for (int w = 0; w < vs::kMaskWords; ++w) {
+      reqw[w] = req[w];
+      if (req[w]) use_mask = true;
+    }
+  if (use_mask && !ix->mask) {
+    // filter requested but no row carries any bit: nothing can match
+    CU(vs::launch_fill_empty(out_s, out_r, (int64_t)B * k, st));
+    return VS_OK;
+  }
+  int path = mode;
+  if (path == VS_Q_AUTO)
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxFusedK && vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
+  if (path == VS_Q_TENSOR) {
+    if (ix->dtype != VS_BF16) return fail(VS_ERR_UNSUPPORTED, "tensor path needs bf16 storage");
+    if (k > vs::kMaxFusedK) return fail(VS_ERR_UNSUPPORTED, "tensor path supports k <= %d", vs::kMaxFusedK);
+    if (!vs::tensor_path_available()) return fail(VS_ERR_UNSUPPORTED, "tensor path not built");
+    vs::TensorArgs ta;
+    ta.rows = ix->rows;
+    ta.inv_norm = ix->inv;
+    ta.mask = use_mask ? ix->mask : nullptr;
+    memcpy(ta.req, reqw, sizeof(reqw));
+    ta.dim = ix->dim;
+    ta.ld_elems = ix->ld;
+    ta.n_rows = ix->n;
+    ta.row_base = ix->row_base;
+    CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B, ix->dim, k, ix->sm_count)));
+    CU(vs::launch_tensor_topk(ta, q_dev, B, k, ix->d_tensor.p, out_s, out_r, ix->sm_count, st));
+    ix->last_path = VS_Q_TENSOR;
+    return VS_OK;
+  }
+  // ---- scan path ----
+  const int64_t ld_bytes = ix->ld * ix->esize;
+  if (vs::scan_rows_per_tile(ix->dtype, ld_bytes) < 0)
+    return fail(VS_ERR_UNSUPPORTED, "row pitch %lld bytes exceeds the scan kernel's 4096-byte limit", (long long)ld_bytes);
+  const bool large_k = k > vs::kMaxFusedK;
+  const int step = large_k ? 4 : kScanBatch;
+  if (!large_k) {
+    CU(ix->d_part_s.reserve((size_t)step * ix->sm_count * k * sizeof(float)));
+    CU(ix->d_part_r.reserve((size_t)step * ix->sm_count * k * sizeof(uint32_t)));
+  } else {
+    CU(ix->d_scores.reserve((size_t)step * ix->n * sizeof(float)));
+    CU(ix->d_select.reserve(vs::select_workspace_bytes(step)));
+  }
+  if (ix->tickets_n < (size_t)kScanBatch) {
+    CU(ix->d_tickets.reserve(kScanBatch * sizeof(unsigned int)));
+    CU(cudaMemsetAsync(ix->d_tickets.p, 0, ix->d_tickets.bytes, st));
+    ix->tickets_n = kScanBatch;
+  }
+  for (int b0 = 0; b0 < B; b0 += step) {
+    const int nb = B - b0 < step ? B - b0 : step;
+    vs::ScanArgs a;
+    a.rows = ix->rows;
+    a.inv_norm = ix->inv;
+    a.mask = use_mask ? ix->mask : nullptr;
+    memcpy(a.req, reqw, sizeof(reqw));
+    a.q = q_dev + (size_t)b0 * ix->dim;
+    a.B = nb;
+    a.dim = ix->dim;
+    a.dtype = ix->dtype;
+    a.k = k;
+    a.ld_bytes = ld_bytes;
+    a.n_rows = ix->n;
+    a.row_base = ix->row_base;
+    a.part_s = (float*)ix->d_part_s.p;
+    a.part_r = (uint32_t*)ix->d_part_r.p;
+    a.tickets = (unsigned int*)ix->d_tickets.p;
+    a.grid_x = ix->sm_count;
+    a.out_s = out_s + (size_t)b0 * k;
+    a.out_r = out_r + (size_t)b0 * k;
+    a.scores_full = large_k ? (float*)ix->d_scores.p : nullptr;
+    CU(vs::launch_scan(a, ix->sm_count, st));
+    if (large_k)
+      CU(vs::launch_select((const float*)ix->d_scores.p, ix->n, nb, k, ix->row_base, ix->d_select.p, a.out_s, a.out_r, st));
+  }
+  ix->last_path = VS_Q_SCAN;
+  return VS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vs_last_error(void) { return g_err; }
+int vs_abi_version(void) { return 1; }
+uint64_t vs_launch_count(void) { return vs::g_launches.load(); }
+
+int vs_create(int device, int dim, int dtype, int64_t capacity_rows, vs_index_t** out) {
+  if (!out) return fail(VS_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (dim <= 0 || dim > 65536) return fail(VS_ERR_ARG, "dim=%d out of range", dim);
+  if (dtype != VS_F32 && dtype != VS_BF16) return fail(VS_ERR_ARG, "dtype must be VS_F32 or VS_BF16");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(VS_ERR_CUDA, "no CUDA device (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(VS_ERR_ARG, "device %d not in [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(VS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  vs_index* ix = new (std::nothrow) vs_index();
+  if (!ix) return fail(VS_ERR_OOM, "host allocation failed");
+  ix->device = device;
+  ix->dim = dim;
+  ix->dtype = dtype;
+  ix->esize = dtype == VS_F32 ? 4 : 2;
+  ix->ld = pitch_elems(dim, ix->esize);
+  ix->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ix;
+    return fail(VS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  if (capacity_rows > 0) {
+    int rc = grow(ix, capacity_rows);
+    if (rc) {
+      cudaStreamDestroy(ix->stream);
+      delete ix;
+      return rc;
+    }
+  }
+  *out = ix;
+  return VS_OK;
+}
+
+int vs_destroy(vs_index_t* ix) {
+  if (!ix) return VS_OK;
+  DeviceGuard g(ix->device);
+  cudaStreamSynchronize(ix->stream);
+  if (ix->rows) cudaFree(ix->rows);
+  if (ix->inv) cudaFree(ix->inv);
+  if (ix->mask) cudaFree(ix->mask);
+  DevBuf* bufs[] = {&ix->d_q,       &ix->d_out_s,  &ix->d_out_r,  &ix->d_part_s, &ix->d_part_r, &ix->d_tickets,
+                    &ix->d_scores,  &ix->d_select, &ix->d_tensor, &ix->d_stage,  &ix->d_misc};
+  for (DevBuf* b : bufs) b->release();
+  ix->h_in.release();
+  ix->h_out.release();
+  cudaStreamDestroy(ix->stream);
+  delete ix;
+  return VS_OK;
+}
+
+int64_t vs_count(const vs_index_t* ix) { return ix ? ix->n : 0; }
+int vs_dim(const vs_index_t* ix) { return ix ? ix->dim : 0; }
+int vs_dtype(const vs_index_t* ix) { return ix ? ix->dtype : -1; }
+int vs_last_query_path(const vs_index_t* ix) { return ix ? ix->last_path : 0; }
+int vs_device_sm_count(const vs_index_t* ix) { return ix ? ix->sm_count : 0; }
+
+int vs_set_row_base(vs_index_t* ix, int64_t row_base) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  ix->row_base = row_base;
+  return VS_OK;
+}
+
+int vs_add_dev(vs_index_t* ix, const float* rows_dev, int64_t n, int64_t* first_row, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (n < 0 || (n > 0 && !rows_dev)) return fail(VS_ERR_ARG, "bad rows/n");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  if (first_row) *first_row = ix->n;
+  if (n == 0) return VS_OK;
+  if (ix->n + n > 0xFFFFFFF0LL) return fail(VS_ERR_ARG, "shard would exceed 2^32 rows");
+  int rc = grow(ix, ix->n + n);
+  if (rc) return rc;
+  cudaStream_t st = pick_stream(ix, stream);
+  char* dst = (char*)ix->rows + (size_t)ix->n * ix->ld * ix->esize;
+  CU(vs::launch_ingest(rows_dev, n, ix->dim, ix->dtype, dst, ix->ld, ix->inv + ix->n, st));
+  if (ix->mask) CU(cudaMemsetAsync(ix->mask + (size_t)ix->n * vs::kMaskWords, 0, (size_t)n * vs::kMaskWords * 8, st));
+  ix->n += n;
+  return VS_OK;
+}
+
+int vs_add_host(vs_index_t* ix, const float* rows, int64_t n, int64_t* first_row) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (n < 0 || (n > 0 && !rows)) return fail(VS_ERR_ARG, "bad rows/n");
+  if (n == 0) {
+    if (first_row) *first_row = ix->n;
+    return VS_OK;
+  }
+  // stage through a device buffer in chunks of <= 64 MiB
+  const int64_t chunk_rows = (64LL << 20) / ((int64_t)ix->dim * 4) > 0 ? (64LL << 20) / ((int64_t)ix->dim * 4) : 1;
+  int64_t first = -1;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t nr = n - r0 < chunk_rows ? n - r0 : chunk_rows;
+    {
+      std::lock_guard<std::mutex> lk(ix->mu);
+      DeviceGuard g(ix->device);
+      CU(ix->d_stage.reserve((size_t)nr * ix->dim * 4));
+      CU(cudaMemcpyAsync(ix->d_stage.p, rows + (size_t)r0 * ix->dim, (size_t)nr * ix->dim * 4, cudaMemcpyHostToDevice,
+                         ix->stream));
+    }
+    int64_t fr = 0;
+    int rc = vs_add_dev(ix, (const float*)ix->d_stage.p, nr, &fr, nullptr);
+    if (rc) return rc;
+    {
+      DeviceGuard g(ix->device);
+      CU(cudaStreamSynchronize(ix->stream));
+    }
+    if (first < 0) first = fr;
+  }
+  if (first_row) *first_row = first;
+  return VS_OK;
+}
+
+int vs_remove(vs_index_t* ix, int64_t row, int64_t* moved_from) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (row < 0 || row >= ix->n) return fail(VS_ERR_ARG, "row %lld out of range [0,%lld)", (long long)row, (long long)ix->n);
+  DeviceGuard g(ix->device);
+  const int64_t last = ix->n - 1;
+  if (moved_from) *moved_from = row == last ? -1 : last;
+  if (row != last) {
+    const size_t rb = (size_t)ix->ld * ix->esize;
+    CU(cudaMemcpyAsync((char*)ix->rows + row * rb, (char*)ix->rows + last * rb, rb, cudaMemcpyDeviceToDevice, ix->stream));
+    CU(cudaMemcpyAsync(ix->inv + row, ix->inv + last, sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    if (ix->mask)
+      CU(cudaMemcpyAsync(ix->mask + row * vs::kMaskWords, ix->mask + last * vs::kMaskWords, vs::kMaskWords * 8,
+                         cudaMemcpyDeviceToDevice, ix->stream));
+  }
+  if (ix->mask) CU(cudaMemsetAsync(ix->mask + last * vs::kMaskWords, 0, vs::kMaskWords * 8, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  ix->n = last;
+  return VS_OK;
+}
+
+int vs_clear(vs_index_t* ix) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  if (ix->mask && ix->n > 0) CU(cudaMemsetAsync(ix->mask, 0, (size_t)ix->n * vs::kMaskWords * 8, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  ix->n = 0;
+  return VS_OK;
+}
+
+int vs_set_mask_bits(vs_index_t* ix, int64_t row, const uint64_t bits[VS_MASK_WORDS]) {
+  if (!ix || !bits) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (row < 0 || row >= ix->n) return fail(VS_ERR_ARG, "row %lld out of range", (long long)row);
+  DeviceGuard g(ix->device);
+  int rc = ensure_mask(ix);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ix->mask + row * vs::kMaskWords, bits, vs::kMaskWords * 8, cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
+int vs_get_mask_bits(const vs_index_t* cix, int64_t row, uint64_t bits[VS_MASK_WORDS]) {
+  vs_index* ix = const_cast<vs_index*>(cix);
+  if (!ix || !bits) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (row < 0 || row >= ix->n) return fail(VS_ERR_ARG, "row %lld out of range", (long long)row);
+  memset(bits, 0, vs::kMaskWords * 8);
+  if (!ix->mask) return VS_OK;
+  DeviceGuard g(ix->device);
+  CU(cudaMemcpyAsync(bits, ix->mask + row * vs::kMaskWords, vs::kMaskWords * 8, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
+int vs_get_rows_host(const vs_index_t* cix, int64_t first_row, int64_t n, float* out) {
+  vs_index* ix = const_cast<vs_index*>(cix);
+  if (!ix || (!out && n > 0)) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (first_row < 0 || n < 0 || first_row + n > ix->n) return fail(VS_ERR_ARG, "row range out of bounds");
+  if (n == 0) return VS_OK;
+  DeviceGuard g(ix->device);
+  CU(ix->d_stage.reserve((size_t)n * ix->dim * 4));
+  const char* src = (const char*)ix->rows + (size_t)first_row * ix->ld * ix->esize;
+  CU(vs::launch_export(src, n, ix->dim, ix->dtype, ix->ld, (float*)ix->d_stage.p, ix->stream));
+  CU(cudaMemcpyAsync(out, ix->d_stage.p, (size_t)n * ix->dim * 4, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
+int vs_query_topk_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits, int mode,
+                      float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B < 0 || (B > 0 && (!q_dev || !out_scores_dev || !out_rows_dev))) return fail(VS_ERR_ARG, "NULL buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  return query_dev_locked(ix, q_dev, B, k, require_bits, mode, out_scores_dev, out_rows_dev, pick_stream(ix, stream));
+}
+
+int vs_query_topk_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits, int mode,
+                       float* out_scores, int64_t* out_rows) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B < 0 || (B > 0 && (!q || !out_scores || !out_rows))) return fail(VS_ERR_ARG, "NULL buffer");
+  if (B == 0) return VS_OK;
+  if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  const size_t qbytes = (size_t)B * ix->dim * 4, sbytes = (size_t)B * k * 4, rbytes = (size_t)B * k * 8;
+  CU(ix->d_q.reserve(qbytes));
+  CU(ix->d_out_s.reserve(sbytes));
+  CU(ix->d_out_r.reserve(rbytes));
+  CU(ix->h_in.reserve(qbytes));
+  CU(ix->h_out.reserve(sbytes + rbytes));
+  memcpy(ix->h_in.p, q, qbytes);  // pinned staging so the H2D copy is a true async DMA
+  CU(cudaMemcpyAsync(ix->d_q.p, ix->h_in.p, qbytes, cudaMemcpyHostToDevice, ix->stream));
+  int rc = query_dev_locked(ix, (const float*)ix->d_q.p, B, k, require_bits, mode, (float*)ix->d_out_s.p,
+                            (int64_t*)ix->d_out_r.p, ix->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ix->h_out.p, ix->d_out_s.p, sbytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync((char*)ix->h_out.p + sbytes, ix->d_out_r.p, rbytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  memcpy(out_scores, ix->h_out.p, sbytes);
+  memcpy(out_rows, (char*)ix->h_out.p + sbytes, rbytes);
+  return VS_OK;
+}
+
+int vs_blend_dev(vs_index_t* ix, const float* img_dev, const float* txt_dev, const double* w_dev, int B, float* out_dev,
+                 void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B < 0 || (B > 0 && (!img_dev || !txt_dev || !w_dev || !out_dev))) return fail(VS_ERR_ARG, "NULL buffer");
+  DeviceGuard g(ix->device);
+  CU(vs::launch_blend(img_dev, txt_dev, w_dev, B, ix->dim, out_dev, pick_stream(ix, stream)));
+  return VS_OK;
+}
+
+int vs_query_multimodal_host(vs_index_t* ix, const float* img, const float* txt, const double* w, int B, int k,
+                             const uint64_t* require_bits, int mode, float* out_scores, int64_t* out_rows) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B < 0 || (B > 0 && (!img || !txt || !w || !out_scores || !out_rows))) return fail(VS_ERR_ARG, "NULL buffer");
+  if (B == 0) return VS_OK;
+  if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  const size_t qbytes = (size_t)B * ix->dim * 4, wbytes = (size_t)B * 8;
+  const size_t sbytes = (size_t)B * k * 4, rbytes = (size_t)B * k * 8;
+  // device staging: [img | txt | blended] in d_stage, weights in d_misc
+  CU(ix->d_stage.reserve(3 * qbytes));
+  CU(ix->d_misc.reserve(wbytes));
+  CU(ix->d_out_s.reserve(sbytes));
+  CU(ix->d_out_r.reserve(rbytes));
+  CU(ix->h_in.reserve(2 * qbytes + wbytes));
+  CU(ix->h_out.reserve(sbytes + rbytes));
+  char* hin = (char*)ix->h_in.p;
+  memcpy(hin, img, qbytes);
+  memcpy(hin + qbytes, txt, qbytes);
+  memcpy(hin + 2 * qbytes, w, wbytes);
+  char* dst = (char*)ix->d_stage.p;
+  CU(cudaMemcpyAsync(dst, hin, 2 * qbytes, cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->d_misc.p, hin + 2 * qbytes, wbytes, cudaMemcpyHostToDevice, ix->stream));
+  float* blended = (float*)(dst + 2 * qbytes);
+  CU(vs::launch_blend((const float*)dst, (const float*)(dst + qbytes), (const double*)ix->d_misc.p, B, ix->dim, blended,
+                      ix->stream));
+  int rc = query_dev_locked(ix, blended, B, k, require_bits, mode, (float*)ix->d_out_s.p, (int64_t*)ix->d_out_r.p,
+                            ix->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ix->h_out.p, ix->d_out_s.p, sbytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync((char*)ix->h_out.p + sbytes, ix->d_out_r.p, rbytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  memcpy(out_scores, ix->h_out.p, sbytes);
+  memcpy(out_rows, (char*)ix->h_out.p + sbytes, rbytes);
+  return VS_OK;
+}
+
+int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int G, int B, int k,
+                      float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (!cand_scores_dev || !cand_rows_dev || !out_scores_dev || !out_rows_dev) return fail(VS_ERR_ARG, "NULL buffer");
+  if (G <= 0 || B <= 0 || k <= 0 || (int64_t)G * k > 16384) return fail(VS_ERR_ARG, "G*k must be in [1,16384]");
+  cudaStream_t st = stream ? (cudaStream_t)stream : (ix ? ix->stream : (cudaStream_t) nullptr);
+  if (ix) {
+    DeviceGuard g(ix->device);
+    CU(vs::launch_merge(cand_scores_dev, cand_rows_dev, G, B, k, out_scores_dev, out_rows_dev, st));
+  } else {
+    CU(vs::launch_merge(cand_scores_dev, cand_rows_dev, G, B, k, out_scores_dev, out_rows_dev, st));
+  }
+  return VS_OK;
+}
+
+int64_t vs_filter_words(const vs_index_t* ix) {
+  if (!ix) return 0;
+  const int64_t w = (ix->n + 31) / 32;
+  return (w + 3) / 4 * 4;
+}
+
+int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float tau, uint32_t* out_bits_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (F <= 0 || !prompts_dev || !out_bits_dev) return fail(VS_ERR_ARG, "bad arguments");
+  if (ix->dtype != VS_BF16) return fail(VS_ERR_UNSUPPORTED, "filter sweep needs bf16 storage (tcgen05 path)");
+  if (!vs::tensor_path_available()) return fail(VS_ERR_UNSUPPORTED, "tensor path not built");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  if (ix->n == 0) return VS_OK;
+  vs::TensorArgs ta;
+  ta.rows = ix->rows;
+  ta.inv_norm = ix->inv;
+  ta.mask = nullptr;
+  memset(ta.req, 0, sizeof(ta.req));
+  ta.dim = ix->dim;
+  ta.ld_elems = ix->ld;
+  ta.n_rows = ix->n;
+  ta.row_base = ix->row_base;
+  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(F, ix->dim, 1, ix->sm_count)));
+  CU(vs::launch_tensor_filter(ta, prompts_dev, F, tau, ix->d_tensor.p, out_bits_dev, vs_filter_words(ix), ix->sm_count,
+                              pick_stream(ix, stream)));
+  return VS_OK;
+}
+
+int vs_filter_sweep_host(vs_index_t* ix, const float* prompts, int F, float tau, uint32_t* out_bits) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (F <= 0 || !prompts || !out_bits) return fail(VS_ERR_ARG, "bad arguments");
+  const size_t pbytes = (size_t)F * ix->dim * 4;
+  const size_t obytes = (size_t)F * vs_filter_words(ix) * 4;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    CU(ix->d_q.reserve(pbytes));
+    CU(ix->d_misc.reserve(obytes + 16));
+    CU(cudaMemcpyAsync(ix->d_q.p, prompts, pbytes, cudaMemcpyHostToDevice, ix->stream));
+  }
+  int rc = vs_filter_sweep_dev(ix, (const float*)ix->d_q.p, F, tau, (uint32_t*)ix->d_misc.p, nullptr);
+  if (rc) return rc;
+  DeviceGuard g(ix->device);
+  CU(cudaMemcpyAsync(out_bits, ix->d_misc.p, obytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
+int vs_dedup_dev(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int64_t cap, int64_t* out_i_dev,
+                 int64_t* out_j_dev, float* out_score_dev, unsigned long long* out_count_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (!out_i_dev || !out_j_dev || !out_score_dev || !out_count_dev || cap < 0) return fail(VS_ERR_ARG, "bad arguments");
+  if (ix->dtype != VS_BF16) return fail(VS_ERR_UNSUPPORTED, "dedup needs bf16 storage (tcgen05 path)");
+  if (!vs::tensor_path_available()) return fail(VS_ERR_UNSUPPORTED, "tensor path not built");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  if (row_lo < 0) row_lo = 0;
+  if (row_hi > ix->n) row_hi = ix->n;
+  cudaStream_t st = pick_stream(ix, stream);
+  CU(cudaMemsetAsync(out_count_dev, 0, sizeof(unsigned long long), st));
+  if (row_lo >= row_hi) return VS_OK;
+  vs::TensorArgs ta;
+  ta.rows = ix->rows;
+  ta.inv_norm = ix->inv;
+  ta.mask = nullptr;
+  memset(ta.req, 0, sizeof(ta.req));
+  ta.dim = ix->dim;
+  ta.ld_elems = ix->ld;
+  ta.n_rows = ix->n;
+  ta.row_base = ix->row_base;
+  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(128, ix->dim, 1, ix->sm_count)));
+  CU(vs::launch_tensor_dedup(ta, row_lo, row_hi, tau, cap, out_i_dev, out_j_dev, out_score_dev, out_count_dev,
+                             ix->d_tensor.p, ix->sm_count, st));
+  return VS_OK;
+}
+
+int vs_dedup_host(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int64_t cap, int64_t* out_i, int64_t* out_j,
+                  float* out_score, int64_t* out_count) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (!out_i || !out_j || !out_score || !out_count || cap < 0) return fail(VS_ERR_ARG, "bad arguments");
+  void* buf = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    CU(ix->d_misc.reserve((size_t)cap * 20 + 64));
+    buf = ix->d_misc.p;
+  }
+  unsigned long long* d_count = (unsigned long long*)buf;
+  int64_t* d_i = (int64_t*)((char*)buf + 16);
+  int64_t* d_j = d_i + cap;
+  float* d_s = (float*)(d_j + cap);
+  int rc = vs_dedup_dev(ix, row_lo, row_hi, tau, cap, d_i, d_j, d_s, d_count, nullptr);
+  if (rc) return rc;
+  DeviceGuard g(ix->device);
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  *out_count = (int64_t)cnt;
+  const int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
+  if (m > 0) {
+    CU(cudaMemcpyAsync(out_i, d_i, m * 8, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(out_j, d_j, m * 8, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(out_score, d_s, m * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+  }
+  if ((int64_t)cnt > cap) return fail(VS_ERR_OVERFLOW, "found %lld pairs, capacity %lld", (long long)cnt, (long long)cap);
+  return VS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vs {
+
+constexpr int kMaskWords = 4;
+constexpr int kMaxFusedK = 128;   // register-list top-k limit of the fused kernels
+constexpr int kMaxK = 1024;
+
+void count_launch(int n = 1);
+
+// ---- K6 ingest: f32 rows -> storage dtype + inverse norms -------------------------------
+cudaError_t launch_ingest(const float* src, int64_t n, int dim, int dtype, void* dst_rows, int64_t ld_elems,
+                          float* dst_inv, cudaStream_t st);
+// storage -> f32 (Collection.get(include=["embeddings"]), persistence)
+cudaError_t launch_export(const void* rows, int64_t n, int dim, int dtype, int64_t ld_elems, float* dst,
+                          cudaStream_t st);
+// multimodal blend (backend/app/main.py:850-860) for B triples
+cudaError_t launch_blend(const float* img, const float* txt, const double* w, int B, int dim, float* out,
+                         cudaStream_t st);
+
+// empty result slots: score = -inf, row = -1
+cudaError_t launch_fill_empty(float* s, int64_t* r, int64_t n, cudaStream_t st);
+
+// ---- K1 scan: fused normalise + GEMV + top-k (HBM-bound) ---------------------------------
+struct ScanArgs {
+  const void* rows;
+  const float* inv_norm;
+  const uint64_t* mask;      // [n][kMaskWords] or nullptr
+  uint64_t req[kMaskWords];  // required bits (all zero = no filter)
+  const float* q;            // [B][dim] raw f32 queries (device)
+  int B, dim, dtype, k;
+  int64_t ld_bytes;          // row pitch in bytes (multiple of 16)
+  int64_t n_rows;
+  int64_t row_base;
+  // workspace (device): partial lists [B][grid][k], tickets [B]
+  float* part_s;
+  uint32_t* part_r;
+  unsigned int* tickets;
+  int grid_x;                // CTAs per query (<= SM count); workspace is sized for it
+  // outputs (device)
+  float* out_s;              // [B][k]
+  int64_t* out_r;            // [B][k]
+  float* scores_full;        // [B][n_rows] when materialising for the large-k path, else nullptr
+};
+// returns cudaErrorInvalidValue when (dtype, ld_bytes) has no instantiation
+cudaError_t launch_scan(const ScanArgs& a, int sm_count, cudaStream_t st);
+int scan_rows_per_tile(int dtype, int64_t ld_bytes);
+
+// ---- K5 merge / select --------------------------------------------------------------------
+// [G][B][k] candidates (global rows, <0 empty) -> [B][k]
+cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
+                         cudaStream_t st);
+// exact top-k (k <= 1024) of materialised scores [B][n] -> [B][k]; workspace: see select_workspace_bytes
+size_t select_workspace_bytes(int B);
+cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, void* workspace,
+                          float* out_s, int64_t* out_r, cudaStream_t st);
+
+// ---- K2/K3/K4 tcgen05 kernels (bf16 storage) -------------------------------------------------
+struct TensorArgs {
+  const void* rows;          // bf16 [n][ld]
+  const float* inv_norm;
+  const uint64_t* mask;
+  uint64_t req[kMaskWords];
+  int dim;
+  int64_t ld_elems;
+  int64_t n_rows;
+  int64_t row_base;
+};
+// queries: f32 [B][dim] raw (normalised + rounded to bf16 on device into q_bf16 workspace)
+size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count);
+cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k, void* workspace, float* out_s,
+                               int64_t* out_r, int sm_count, cudaStream_t st);
+cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int F, float tau, void* workspace,
+                                 uint32_t* out_bits, int64_t words_per_filter, int sm_count, cudaStream_t st);
+cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row_hi, float tau, int64_t cap,
+                                int64_t* out_i, int64_t* out_j, float* out_score, unsigned long long* out_count,
+                                void* workspace, int sm_count, cudaStream_t st);
+bool tensor_path_available();
+
+}  // namespace vs

@@ -1,0 +1,368 @@
+// misc_kernels.cu -- K6 ingest (cast + inverse norm), export, multimodal blend, K5 candidate
+// merge (block bitonic), and the exact radix select used for k > 128.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+
+// ------------------------------------------------------------------------------------------
+// K6 ingest.  Collection.add (backend/app/main.py:735-740): one warp per row; the row is cast
+// to the storage dtype, the pad up to the pitch is zeroed, and 1/(||stored row|| + 1e-30) is
+// written beside it (hnswlib's cosine space normalises at insert the same way).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float store_elem(T* dst, float v);
+template <>
+__device__ __forceinline__ float store_elem<float>(float* dst, float v) {
+  *dst = v;
+  return v;
+}
+template <>
+__device__ __forceinline__ float store_elem<__nv_bfloat16>(__nv_bfloat16* dst, float v) {
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  *dst = b;
+  return __bfloat162float(b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_kernel(const float* __restrict__ src, int64_t n, int dim, T* __restrict__ dst,
+                                                     int64_t ld, float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n; row += nwarps) {
+    const float* s = src + row * dim;
+    T* d = dst + row * ld;
+    float ss = 0.f;
+    for (int e = lane; e < (int)ld; e += 32) {
+      const float v = e < dim ? s[e] : 0.f;
+      const float r = store_elem<T>(d + e, v);
+      ss = fmaf(r, r, ss);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if (lane == 0) inv[row] = 1.0f / (sqrtf(ss) + 1e-30f);
+  }
+}
+
+cudaError_t launch_ingest(const float* src, int64_t n, int dim, int dtype, void* dst_rows, int64_t ld_elems,
+                          float* dst_inv, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t blocks = min((int64_t)148 * 8, (n + 7) / 8);
+  if (dtype == 0)
+    ingest_kernel<float><<<(int)blocks, 256, 0, st>>>(src, n, dim, static_cast<float*>(dst_rows), ld_elems, dst_inv);
+  else
+    ingest_kernel<__nv_bfloat16>
+        <<<(int)blocks, 256, 0, st>>>(src, n, dim, static_cast<__nv_bfloat16*>(dst_rows), ld_elems, dst_inv);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) export_kernel(const T* __restrict__ rows, int64_t n, int dim, int64_t ld,
+                                                     float* __restrict__ dst) {
+  const int64_t total = n * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    const int e = (int)(i - r * dim);
+    dst[i] = (float)rows[r * ld + e];
+  }
+}
+
+cudaError_t launch_export(const void* rows, int64_t n, int dim, int dtype, int64_t ld_elems, float* dst,
+                          cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t blocks = min((int64_t)148 * 8, (n * dim + 255) / 256);
+  if (dtype == 0)
+    export_kernel<float><<<(int)blocks, 256, 0, st>>>(static_cast<const float*>(rows), n, dim, ld_elems, dst);
+  else
+    export_kernel<__nv_bfloat16>
+        <<<(int)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(rows), n, dim, ld_elems, dst);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// multimodal blend, search_multimodal (backend/app/main.py:850-860): one warp per query pair.
+//   i^ = i/||i||, t^ = t/||t||, c = w*i^ + (1-w)*t^, out = c/||c||      (all float32)
+// Same statement order as the reference's numpy code so the result matches it to rounding of
+// the norm reductions.  No zero-norm guard there either; here a zero norm yields zeros.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+                                                    const double* __restrict__ w, int B, int dim, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float* ip = img + (size_t)b * dim;
+  const float* tp = txt + (size_t)b * dim;
+  float si = 0.f, stt = 0.f;
+  for (int e = lane; e < dim; e += 32) {
+    si = fmaf(ip[e], ip[e], si);
+    stt = fmaf(tp[e], tp[e], stt);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    si += __shfl_xor_sync(0xffffffffu, si, off);
+    stt += __shfl_xor_sync(0xffffffffu, stt, off);
+  }
+  const float ni = sqrtf(si), nt = sqrtf(stt);
+  // numpy semantics of the reference: the python-float weight and (1 - weight) are each
+  // rounded to float32 once, then multiplied in float32.
+  const float wi = (float)w[b], wt = (float)(1.0 - w[b]);
+  float sc = 0.f;
+  for (int e = lane; e < dim; e += 32) {
+    const float c = wi * (ni > 0.f ? ip[e] / ni : 0.f) + wt * (nt > 0.f ? tp[e] / nt : 0.f);
+    out[(size_t)b * dim + e] = c;
+    sc = fmaf(c, c, sc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);
+  const float nc = sqrtf(sc);
+  __syncwarp();
+  for (int e = lane; e < dim; e += 32) {
+    const float c = out[(size_t)b * dim + e];
+    out[(size_t)b * dim + e] = nc > 0.f ? c / nc : 0.f;
+  }
+}
+
+__global__ void fill_empty_kernel(float* s, int64_t* r, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    s[i] = VS_NEG_INF;
+    r[i] = -1;
+  }
+}
+cudaError_t launch_fill_empty(float* s, int64_t* r, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  fill_empty_kernel<<<(int)min((int64_t)592, (n + 255) / 256), 256, 0, st>>>(s, r, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blend(const float* img, const float* txt, const double* w, int B, int dim, float* out,
+                         cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  blend_kernel<<<(B + 7) / 8, 256, 0, st>>>(img, txt, w, B, dim, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: merge of per-shard candidates after the all-gather.  One CTA per query; candidates get a
+// unique 64-bit key (orderable score << 32 | ~position); positions are (shard, rank) ordered,
+// which for equal scores is the same as global-row order because shards are contiguous row
+// ranges in rank order.  Block bitonic sort in shared memory, descending.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ cr, int G,
+                                                     int B, int k, int P, float* __restrict__ out_s,
+                                                     int64_t* __restrict__ out_r) {
+  extern __shared__ __align__(16) uint64_t keys[];
+  const int b = blockIdx.x;
+  const int C = G * k;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) {
+    uint64_t key = 0;
+    if (c < C) {
+      const int g = c / k, e = c - g * k;
+      const size_t src = ((size_t)g * B + b) * k + e;
+      const float s = cs[src];
+      if (cr[src] >= 0 && s == s) key = ((uint64_t)score_key(s) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)c);
+    }
+    keys[c] = key;
+  }
+  bitonic_sort_desc(keys, P);
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    const uint64_t key = e < P ? keys[e] : 0;
+    float s = VS_NEG_INF;
+    int64_t r = -1;
+    if (key != 0) {
+      const int c = (int)(0xFFFFFFFFu - (uint32_t)key);
+      const int g = c / k, ee = c - g * k;
+      const size_t src = ((size_t)g * B + b) * k + ee;
+      s = cs[src];
+      r = cr[src];
+    }
+    out_s[(size_t)b * k + e] = s;
+    out_r[(size_t)b * k + e] = r;
+  }
+}
+
+cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
+                         cudaStream_t st) {
+  if (G <= 0 || B <= 0 || k <= 0) return cudaErrorInvalidValue;
+  int P = 2;
+  while (P < G * k) P <<= 1;
+  if (P > 16384) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)P * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
+  merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, B, k, P, out_s, out_r);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact select for k > 128 (the UI's "All" = 1000, backend/app/main.py:757) over materialised
+// scores.  Every row gets the unique key (orderable score << 32 | ~row); six MSB-first radix
+// passes (11,11,10,11,11,10 bits) pin down the k-th largest key exactly -- ties in score are
+// resolved by row index inside the key, so exactly k rows satisfy key >= threshold.  The last
+// CTA of each pass (ticket) picks the digit; the last CTA of the compaction pass sorts.
+// ------------------------------------------------------------------------------------------
+constexpr int kSelBins = 2048;
+struct SelectState {
+  unsigned long long prefix;   // known high bits of the threshold key
+  unsigned long long known;    // mask of known bits
+  unsigned int k_rem;          // how many keys still to take from the matching set
+  unsigned int ticket;
+  unsigned int out_count;
+  unsigned int k_eff;
+  unsigned int hist[kSelBins];
+  unsigned long long buf[kMaxK];
+};
+size_t select_workspace_bytes(int B) { return sizeof(SelectState) * (size_t)B; }
+
+__device__ __forceinline__ unsigned long long select_key(float s, uint32_t row) {
+  if (!(s == s)) s = VS_NEG_INF;
+  return ((unsigned long long)score_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - row);
+}
+
+__global__ void __launch_bounds__(256) select_init_kernel(SelectState* st, int B, int k, int64_t n) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  SelectState* s = st + b;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) s->hist[i] = 0;
+  if (threadIdx.x == 0) {
+    s->prefix = 0;
+    s->known = 0;
+    s->k_eff = (unsigned int)min((int64_t)k, n);
+    s->k_rem = s->k_eff;
+    s->ticket = 0;
+    s->out_count = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const float* __restrict__ scores, int64_t n, SelectState* st,
+                                                          int shift, int bits) {
+  __shared__ unsigned int sh[kSelBins];
+  __shared__ int s_last;
+  SelectState* s = st + blockIdx.y;
+  const float* sc = scores + (size_t)blockIdx.y * n;
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned long long prefix = s->prefix, known = s->known;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = select_key(sc[i], (uint32_t)i);
+    if (((key ^ prefix) & known) == 0) atomicAdd(&sh[(unsigned int)(key >> shift) & (nb - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (sh[i]) atomicAdd(&s->hist[i], sh[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&s->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // pick the digit: walk bins from the top until the cumulative count reaches k_rem.
+  // (2048 bins, one thread -- a few microseconds, once per pass.)
+  if (threadIdx.x == 0) {
+    volatile unsigned int* h = s->hist;
+    unsigned int rem = s->k_rem;
+    int d = nb - 1;
+    for (; d > 0; --d) {
+      const unsigned int c = h[d];
+      if (c >= rem) break;
+      rem -= c;
+    }
+    s->k_rem = rem;
+    s->prefix = prefix | ((unsigned long long)d << shift);
+    s->known = known | ((unsigned long long)(nb - 1) << shift);
+    s->ticket = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) s->hist[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) select_compact_kernel(const float* __restrict__ scores, int64_t n, SelectState* st,
+                                                             int k, int64_t row_base, float* __restrict__ out_s,
+                                                             int64_t* __restrict__ out_r) {
+  __shared__ int s_last;
+  __shared__ unsigned long long keys[kMaxK];
+  SelectState* s = st + blockIdx.y;
+  const float* sc = scores + (size_t)blockIdx.y * n;
+  const unsigned long long thr = s->prefix;
+  const unsigned int k_eff = s->k_eff;
+  if (k_eff > 0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const unsigned long long key = select_key(sc[i], (uint32_t)i);
+      if (key >= thr) {
+        const unsigned int slot = atomicAdd(&s->out_count, 1u);
+        if (slot < (unsigned int)kMaxK) s->buf[slot] = key;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&s->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  volatile unsigned long long* gb = s->buf;
+  for (int i = threadIdx.x; i < kMaxK; i += blockDim.x) keys[i] = i < (int)k_eff ? gb[i] : 0ull;
+  bitonic_sort_desc(reinterpret_cast<uint64_t*>(keys), kMaxK);
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    float v = VS_NEG_INF;
+    int64_t r = -1;
+    if (e < (int)k_eff) {
+      const unsigned long long key = keys[e];
+      v = key_score((uint32_t)(key >> 32));
+      if (v != VS_NEG_INF) r = (int64_t)(0xFFFFFFFFu - (uint32_t)key) + row_base;
+    }
+    out_s[(size_t)blockIdx.y * k + e] = v;
+    out_r[(size_t)blockIdx.y * k + e] = r;
+  }
+  if (threadIdx.x == 0) {
+    s->ticket = 0;
+    s->out_count = 0;
+  }
+}
+
+cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, void* workspace,
+                          float* out_s, int64_t* out_r, cudaStream_t st) {
+  if (k > kMaxK || k <= 0 || n <= 0 || n > 0xFFFFFFF0LL) return cudaErrorInvalidValue;
+  SelectState* ss = static_cast<SelectState*>(workspace);
+  select_init_kernel<<<B, 256, 0, st>>>(ss, B, k, n);
+  int gx = (int)min((int64_t)148 * 4, (n + 255) / 256);
+  if (gx < 1) gx = 1;
+  const int shifts[6] = {53, 42, 32, 21, 10, 0};
+  const int bits[6] = {11, 11, 10, 11, 11, 10};
+  for (int pass = 0; pass < 6; ++pass) select_hist_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, ss, shifts[pass], bits[pass]);
+  select_compact_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, ss, k, row_base, out_s, out_r);
+  count_launch(8);
+  return cudaGetLastError();
+}
+
+}  // namespace vs

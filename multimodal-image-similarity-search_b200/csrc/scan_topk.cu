@@ -1,0 +1,380 @@
+// scan_topk.cu -- K1: single-query exact cosine top-k as ONE fused kernel (sm_100a).
+//
+// Replaces the arithmetic of chromadb Collection.query for one vector
+// (reference call site backend/app/main.py:761-765).  The corpus shard streams from HBM
+// exactly once per query:
+//   * a producer thread per CTA moves tiles of R whole rows (R*pitch contiguous bytes) plus
+//     their R inverse norms into a ring of shared-memory stages with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), L2 evict_first;
+//   * 8 consumer warps read the staged rows with conflict-free 128-bit LDS, FMA against the
+//     L2-normalised query held in registers (query normalisation is fused: every warp derives
+//     1/||q|| itself), butterfly-reduce, scale by the row's inverse norm;
+//   * each warp keeps a register-resident sorted top-k list distributed over its lanes
+//     (WarpTopK<M>, k <= 32*M) updated with warp shuffles; nearly every row fails the
+//     `score > k-th` test so the list code is off the hot path;
+//   * filter bits ("pre" mode of the filter pass, backend/app/main.py:215) are only looked
+//     up for rows that would enter the list -- zero extra traffic;
+//   * the per-warp lists are merged per CTA, written to a small global buffer, and the last
+//     CTA to finish (ticket) merges all CTA lists and writes the final [k] result: no second
+//     kernel, no score materialisation.
+// Algorithmic HBM bytes per query = n_rows * (pitch + 4).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 220 * 1024;
+
+// rows per consumer warp per tile, chosen so a stage is <= 32 KB
+__host__ __device__ constexpr int rows_per_warp(int cpl) {
+  return cpl <= 1 ? 8 : cpl <= 2 ? 4 : cpl <= 4 ? 2 : 1;
+}
+
+struct ScanKernelParams {
+  const uint8_t* rows;
+  const float* inv_norm;
+  const uint64_t* mask;
+  uint64_t req[kMaskWords];
+  const float* q;
+  float* part_s;
+  uint32_t* part_r;
+  unsigned int* tickets;
+  float* out_s;
+  int64_t* out_r;
+  float* scores_full;
+  int64_t row_base;
+  uint32_t n_rows;
+  uint32_t n_tiles;
+  int dim;
+  int ld_bytes;
+  int k;
+  int stages;
+  int stage_stride;   // bytes between row stages
+  int use_mask;
+};
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static constexpr int kPerChunk = 4;
+  static __device__ __forceinline__ float dot(const uint4& v, const float* q) {
+    return fmaf(__uint_as_float(v.w), q[3],
+                fmaf(__uint_as_float(v.z), q[2], fmaf(__uint_as_float(v.y), q[1], __uint_as_float(v.x) * q[0])));
+  }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int kPerChunk = 8;
+  // bf16 -> f32 is a 16-bit shift: low half `x << 16`, high half `x & 0xffff0000`
+  static __device__ __forceinline__ float dot(const uint4& v, const float* q) {
+    float a = __uint_as_float(v.x << 16) * q[0];
+    a = fmaf(__uint_as_float(v.x & 0xffff0000u), q[1], a);
+    a = fmaf(__uint_as_float(v.y << 16), q[2], a);
+    a = fmaf(__uint_as_float(v.y & 0xffff0000u), q[3], a);
+    a = fmaf(__uint_as_float(v.z << 16), q[4], a);
+    a = fmaf(__uint_as_float(v.z & 0xffff0000u), q[5], a);
+    a = fmaf(__uint_as_float(v.w << 16), q[6], a);
+    a = fmaf(__uint_as_float(v.w & 0xffff0000u), q[7], a);
+    return a;
+  }
+};
+
+__device__ __forceinline__ bool mask_ok(const uint64_t* mask, uint32_t row, const uint64_t* req) {
+  const uint64_t* m = mask + (size_t)row * kMaskWords;
+  bool ok = true;
+#pragma unroll
+  for (int w = 0; w < kMaskWords; ++w) ok = ok && ((__ldg(m + w) & req[w]) == req[w]);
+  return ok;
+}
+
+// M == 0: materialise scores (large-k path) instead of keeping lists.
+template <typename T, int CPL, int M>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanKernelParams p) {
+  constexpr int EPC = Elem<T>::kPerChunk;
+  constexpr int U = rows_per_warp(CPL);
+  constexpr int R = kConsumerWarps * U;
+  constexpr int ML = M > 0 ? M : 1;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [stages][stage_stride] rows | [kMaxStages][R] inv norms | barriers | candidate lists
+  uint8_t* s_rows = smem;
+  float* s_inv = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_stride);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_inv + kMaxStages * R);
+  uint64_t* empty = full + kMaxStages;
+  float* cand_s = reinterpret_cast<float*>(empty + kMaxStages);
+  uint32_t* cand_r = reinterpret_cast<uint32_t*>(cand_s + kConsumerWarps * 32 * ML);
+  __shared__ int s_is_last;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.y;
+  const int k = p.k;
+  const int chunks = p.ld_bytes >> 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  WarpTopK<ML> top;
+  top.init();
+
+  if (warp == kConsumerWarps) {
+    // ===================== producer: one thread drives the TMA bulk pipeline ==============
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      uint32_t it = 0;
+      for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int st = it % p.stages;
+        const uint32_t use = it / p.stages;
+        if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+        const uint32_t row0 = t * R;
+        const uint32_t nr = min((uint32_t)R, p.n_rows - row0);
+        const uint32_t bytes_rows = nr * (uint32_t)p.ld_bytes;
+        const uint32_t bytes_inv = ((nr + 3u) & ~3u) * 4u;
+        mbar_expect_tx(&full[st], bytes_rows + bytes_inv);
+        bulk_g2s(s_rows + (size_t)st * p.stage_stride, p.rows + (size_t)row0 * p.ld_bytes, bytes_rows, &full[st],
+                 pol);
+        bulk_g2s(s_inv + st * R, p.inv_norm + row0, bytes_inv, &full[st], pol);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== consumers =======================================================
+    // normalised query in registers: chunk c*32+lane of the row <-> q elements [ch*EPC, +EPC)
+    float q[CPL][EPC];
+    {
+      const float* qp = p.q + (size_t)qi * p.dim;
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int e0 = (c * 32 + lane) * EPC;
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) {
+          const float v = (e0 + e < p.dim) ? __ldg(qp + e0 + e) : 0.f;
+          q[c][e] = v;
+          ss = fmaf(v, v, ss);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      const float qinv = 1.0f / (sqrtf(ss) + 1e-30f);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) q[c][e] *= qinv;
+    }
+
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int st = it % p.stages;
+      mbar_wait(&full[st], (it / p.stages) & 1);
+      const uint8_t* tile = s_rows + (size_t)st * p.stage_stride + (size_t)(warp * U) * p.ld_bytes;
+      float acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint4* rp = reinterpret_cast<const uint4*>(tile + (size_t)u * p.ld_bytes);
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const int ch = c * 32 + lane;
+          if (ch < chunks) a += Elem<T>::dot(rp[ch], q[c]);
+        }
+        acc[u] = a;
+      }
+      float inv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) inv[u] = s_inv[st * R + warp * U + u];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+      // all lanes have consumed the stage (the shuffles above are warp-convergent)
+      if (lane == 0) mbar_arrive(&empty[st]);
+
+      const uint32_t row0 = t * R + warp * U;
+      if constexpr (M == 0) {
+        float mine = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (lane == u) mine = acc[u] * inv[u];
+        const uint32_t row = row0 + lane;
+        if (lane < U && row < p.n_rows) {
+          if (p.use_mask && !mask_ok(p.mask, row, p.req)) mine = VS_NEG_INF;
+          p.scores_full[(size_t)qi * p.n_rows + row] = mine;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float s = acc[u] * inv[u];
+          const uint32_t row = row0 + u;
+          // rows arrive in increasing order within a warp, so on equal score the earlier row
+          // stays: a strict compare implements the (score desc, row asc) order here.
+          if (s > top.thr_s && row < p.n_rows) {
+            if (!p.use_mask || mask_ok(p.mask, row, p.req)) top.insert(s, row, k - 1, lane);
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (M == 0) return;
+
+  // ---- per-CTA merge of the 8 warp lists ---------------------------------------------------
+  if (warp < kConsumerWarps) top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+  __syncthreads();
+  const size_t pbase = ((size_t)qi * gridDim.x + blockIdx.x) * k;
+  if (warp == 0) {
+    top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
+    if (gridDim.x == 1) {
+      // single CTA: this is already the answer
+      for (int e = lane; e < k; e += 32) {
+#pragma unroll
+        for (int m = 0; m < ML; ++m)
+          if ((e >> 5) == m) {
+            p.out_s[(size_t)qi * k + e] = top.s[m];
+            p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + p.row_base;
+          }
+      }
+    } else {
+      top.store(p.part_s + pbase, p.part_r + pbase, k, lane);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned int ticket = atomicAdd(&p.tickets[qi], 1u);
+        s_is_last = (ticket == gridDim.x - 1);
+      }
+    }
+  }
+  if (gridDim.x == 1) return;
+  __syncthreads();
+  if (!s_is_last) return;
+
+  // ---- last CTA: merge every CTA's list (8 warps in parallel, then warp 0) -----------------
+  __threadfence();
+  if (warp < kConsumerWarps) {
+    top.init();
+    const volatile float* gs = p.part_s + (size_t)qi * gridDim.x * k;
+    const volatile uint32_t* gr = p.part_r + (size_t)qi * gridDim.x * k;
+    // warp w takes CTA lists w, w+8, ... as one strided batch (32 candidates per round)
+    const int nl = ((int)gridDim.x - warp + kConsumerWarps - 1) / kConsumerWarps;
+    if (nl > 0) top.merge_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
+    top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
+    for (int e = lane; e < k; e += 32) {
+#pragma unroll
+      for (int m = 0; m < ML; ++m)
+        if ((e >> 5) == m) {
+          p.out_s[(size_t)qi * k + e] = top.s[m];
+          p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + p.row_base;
+        }
+    }
+    if (lane == 0) p.tickets[qi] = 0;  // ready for the next launch
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int cpl_for(int64_t ld_bytes) {
+  const int64_t chunks = ld_bytes / 16;
+  const int need = (int)((chunks + 31) / 32);
+  const int avail[] = {1, 2, 3, 4, 6, 8};
+  for (int a : avail)
+    if (need <= a) return a;
+  return -1;
+}
+
+int scan_rows_per_tile(int dtype, int64_t ld_bytes) {
+  (void)dtype;
+  const int cpl = cpl_for(ld_bytes);
+  return cpl < 0 ? -1 : kConsumerWarps * rows_per_warp(cpl);
+}
+
+template <typename T, int CPL, int M>
+static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) {
+  constexpr int U = rows_per_warp(CPL);
+  constexpr int R = kConsumerWarps * U;
+  constexpr int ML = M > 0 ? M : 1;
+  ScanKernelParams p;
+  p.rows = static_cast<const uint8_t*>(a.rows);
+  p.inv_norm = a.inv_norm;
+  p.mask = a.mask;
+  p.use_mask = 0;
+  for (int w = 0; w < kMaskWords; ++w) {
+    p.req[w] = a.req[w];
+    if (a.req[w]) p.use_mask = 1;
+  }
+  if (!a.mask) p.use_mask = 0;
+  p.q = a.q;
+  p.part_s = a.part_s;
+  p.part_r = a.part_r;
+  p.tickets = a.tickets;
+  p.out_s = a.out_s;
+  p.out_r = a.out_r;
+  p.scores_full = a.scores_full;
+  p.row_base = a.row_base;
+  p.n_rows = (uint32_t)a.n_rows;
+  p.n_tiles = (uint32_t)((a.n_rows + R - 1) / R);
+  p.dim = a.dim;
+  p.ld_bytes = (int)a.ld_bytes;
+  p.k = a.k;
+  p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
+  const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;
+  int stages = (kSmemBudget - fixed) / p.stage_stride;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return cudaErrorInvalidValue;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * p.stage_stride + fixed;
+  auto kern = scan_topk_kernel<T, CPL, M>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int gx = a.grid_x > 0 ? a.grid_x : sm_count;
+  if ((uint32_t)gx > p.n_tiles) gx = (int)p.n_tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, a.B, 1);
+  kern<<<grid, kScanThreads, smem, st>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename T, int CPL>
+static cudaError_t launch_m(const ScanArgs& a, int sm_count, cudaStream_t st) {
+  if (a.scores_full) return launch_one<T, CPL, 0>(a, sm_count, st);
+  if (a.k <= 32) return launch_one<T, CPL, 1>(a, sm_count, st);
+  if (a.k <= 128) return launch_one<T, CPL, 4>(a, sm_count, st);
+  return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t launch_t(const ScanArgs& a, int sm_count, cudaStream_t st) {
+  switch (cpl_for(a.ld_bytes)) {
+    case 1: return launch_m<T, 1>(a, sm_count, st);
+    case 2: return launch_m<T, 2>(a, sm_count, st);
+    case 3: return launch_m<T, 3>(a, sm_count, st);
+    case 4: return launch_m<T, 4>(a, sm_count, st);
+    case 6: return launch_m<T, 6>(a, sm_count, st);
+    case 8: return launch_m<T, 8>(a, sm_count, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_scan(const ScanArgs& a, int sm_count, cudaStream_t st) {
+  if (a.n_rows <= 0 || a.B <= 0) return cudaErrorInvalidValue;
+  if (a.ld_bytes % 16 != 0) return cudaErrorInvalidValue;
+  if (a.dtype == 0) return launch_t<float>(a, sm_count, st);
+  return launch_t<__nv_bfloat16>(a, sm_count, st);
+}
+
+}  // namespace vs

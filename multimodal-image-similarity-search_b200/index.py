@@ -1,0 +1,253 @@
+"""DeviceIndex -- one row shard resident in the HBM of one B200, driven through the C ABI.
+
+Host buffers are numpy arrays; device buffers are torch CUDA tensors passed by ``data_ptr()``
+(torch is plumbing for device memory and streams only -- every kernel is in
+``libvecsearch_b200.so``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+_DTYPES = {"f32": N.VS_F32, "fp32": N.VS_F32, "float32": N.VS_F32,
+           "bf16": N.VS_BF16, "bfloat16": N.VS_BF16}
+_MODES = {"auto": N.VS_Q_AUTO, "scan": N.VS_Q_SCAN, "tensor": N.VS_Q_TENSOR}
+
+
+def _bits_array(bits: Optional[Sequence[int]]):
+    """iterable of filter-bit indices -> (uint64 * 4) or None."""
+    if bits is None:
+        return None
+    words = [0] * N.MASK_WORDS
+    for b in bits:
+        if not 0 <= b < 64 * N.MASK_WORDS:
+            raise ValueError(f"filter bit {b} out of range [0,{64 * N.MASK_WORDS})")
+        words[b // 64] |= 1 << (b % 64)
+    return (C.c_uint64 * N.MASK_WORDS)(*words)
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        return 0
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+class DeviceIndex:
+    def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 0, row_base: int = 0):
+        self._lib = N.load()
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self.dim, self.dtype, self.device = int(dim), "bf16" if _DTYPES[dtype] else "f32", int(device)
+        h = C.c_void_p()
+        N.check(self._lib.vs_create(self.device, self.dim, _DTYPES[dtype], int(capacity), C.byref(h)))
+        self._h = h
+        if row_base:
+            self.set_row_base(row_base)
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.vs_count(self._h))
+
+    count = __len__
+
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.vs_device_sm_count(self._h))
+
+    @property
+    def last_query_path(self) -> str:
+        return {N.VS_Q_SCAN: "scan", N.VS_Q_TENSOR: "tensor"}.get(int(self._lib.vs_last_query_path(self._h)), "none")
+
+    def set_row_base(self, row_base: int):
+        N.check(self._lib.vs_set_row_base(self._h, int(row_base)))
+
+    # -- ingest / maintenance ------------------------------------------------------------
+    def add(self, rows) -> int:
+        """Append rows ([n, dim] float32; numpy -> host path, torch CUDA tensor -> device path).
+        Returns the local row number of the first appended row."""
+        first = C.c_int64(-1)
+        if isinstance(rows, np.ndarray) or not hasattr(rows, "data_ptr"):
+            a = np.ascontiguousarray(rows, dtype=np.float32)
+            if a.ndim == 1:
+                a = a[None]
+            if a.ndim != 2 or a.shape[1] != self.dim:
+                raise ValueError(f"expected [n,{self.dim}] rows, got {a.shape}")
+            N.check(self._lib.vs_add_host(self._h, a.ctypes.data, a.shape[0], C.byref(first)))
+        else:
+            import torch
+            t = rows
+            if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != self.dim:
+                raise ValueError("device rows must be a CUDA float32 [n, dim] tensor")
+            t = t.contiguous()
+            st = torch.cuda.current_stream(t.device)
+            N.check(self._lib.vs_add_dev(self._h, _ptr(t), t.shape[0], C.byref(first), _stream_ptr(st)))
+        return int(first.value)
+
+    def remove(self, row: int) -> int:
+        """Remove a row (last row is moved into its place).  Returns the moved row or -1."""
+        moved = C.c_int64(-1)
+        N.check(self._lib.vs_remove(self._h, int(row), C.byref(moved)))
+        return int(moved.value)
+
+    def clear(self):
+        N.check(self._lib.vs_clear(self._h))
+
+    def set_filter_bits(self, row: int, bits: Sequence[int]):
+        N.check(self._lib.vs_set_mask_bits(self._h, int(row), _bits_array(bits)))
+
+    def get_filter_bits(self, row: int):
+        w = (C.c_uint64 * N.MASK_WORDS)()
+        N.check(self._lib.vs_get_mask_bits(self._h, int(row), w))
+        return [b for b in range(64 * N.MASK_WORDS) if (w[b // 64] >> (b % 64)) & 1]
+
+    def get_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), dtype=np.float32)
+        N.check(self._lib.vs_get_rows_host(self._h, int(first), int(n), out.ctypes.data))
+        return out
+
+    # -- query ----------------------------------------------------------------------------
+    def query(self, q, k: int, require_bits: Optional[Sequence[int]] = None, mode: str = "auto"
+              ) -> Tuple[np.ndarray, np.ndarray]:
+        """HOST-buffer query (H2D + kernels + D2H inside): q [B, dim] float32 numpy ->
+        (scores [B,k] float32, rows [B,k] int64); empty slots are (-inf, -1)."""
+        a = np.ascontiguousarray(q, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[None]
+        if a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"expected [B,{self.dim}] queries, got {a.shape}")
+        B = a.shape[0]
+        s = np.empty((B, k), dtype=np.float32)
+        r = np.empty((B, k), dtype=np.int64)
+        N.check(self._lib.vs_query_topk_host(self._h, a.ctypes.data, B, int(k), _bits_array(require_bits),
+                                             _MODES[mode], s.ctypes.data, r.ctypes.data))
+        return s, r
+
+    def query_dev(self, q, k: int, out_scores=None, out_rows=None, require_bits: Optional[Sequence[int]] = None,
+                  mode: str = "auto", stream=None):
+        """DEVICE-buffer query, asynchronous on ``stream`` (default: torch's current stream)."""
+        import torch
+        if q.dim() == 1:
+            q = q[None]
+        if not q.is_cuda or q.dtype != torch.float32 or q.shape[1] != self.dim:
+            raise ValueError("queries must be a CUDA float32 [B, dim] tensor")
+        q = q.contiguous()
+        B = q.shape[0]
+        if out_scores is None:
+            out_scores = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        if out_rows is None:
+            out_rows = torch.empty((B, k), dtype=torch.int64, device=q.device)
+        st = stream if stream is not None else torch.cuda.current_stream(q.device)
+        N.check(self._lib.vs_query_topk_dev(self._h, _ptr(q), B, int(k), _bits_array(require_bits), _MODES[mode],
+                                            _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
+        return out_scores, out_rows
+
+    def query_multimodal(self, img, txt, w, k: int, require_bits: Optional[Sequence[int]] = None,
+                         mode: str = "auto") -> Tuple[np.ndarray, np.ndarray]:
+        """HOST-buffer multimodal query: blend (backend/app/main.py:850-860) on the device, then
+        top-k.  img/txt [B, dim] float32, w [B] (python floats / float64)."""
+        a = np.ascontiguousarray(img, dtype=np.float32)
+        t = np.ascontiguousarray(txt, dtype=np.float32)
+        if a.ndim == 1:
+            a, t = a[None], t[None]
+        ww = np.ascontiguousarray(np.broadcast_to(np.asarray(w, dtype=np.float64), (a.shape[0],)))
+        if a.shape != t.shape or a.shape[1] != self.dim:
+            raise ValueError("img/txt must both be [B, dim]")
+        B = a.shape[0]
+        s = np.empty((B, k), dtype=np.float32)
+        r = np.empty((B, k), dtype=np.int64)
+        N.check(self._lib.vs_query_multimodal_host(self._h, a.ctypes.data, t.ctypes.data, ww.ctypes.data, B, int(k),
+                                                   _bits_array(require_bits), _MODES[mode], s.ctypes.data,
+                                                   r.ctypes.data))
+        return s, r
+
+    def blend_dev(self, img, txt, w, out=None, stream=None):
+        """search_multimodal's blend (backend/app/main.py:850-860) for B (img, txt, w) triples on
+        the device; ``w`` is a float64 CUDA tensor [B]."""
+        import torch
+        B = img.shape[0]
+        if out is None:
+            out = torch.empty((B, self.dim), dtype=torch.float32, device=img.device)
+        st = stream if stream is not None else torch.cuda.current_stream(img.device)
+        N.check(self._lib.vs_blend_dev(self._h, _ptr(img.contiguous()), _ptr(txt.contiguous()),
+                                       _ptr(w.to(torch.float64).contiguous()), B, _ptr(out), _stream_ptr(st)))
+        return out
+
+    def merge_dev(self, cand_scores, cand_rows, out_scores=None, out_rows=None, stream=None):
+        """[G,B,k] gathered candidates -> [B,k] (runs on the candidates' device)."""
+        import torch
+        G, B, k = cand_scores.shape
+        if out_scores is None:
+            out_scores = torch.empty((B, k), dtype=torch.float32, device=cand_scores.device)
+        if out_rows is None:
+            out_rows = torch.empty((B, k), dtype=torch.int64, device=cand_scores.device)
+        st = stream if stream is not None else torch.cuda.current_stream(cand_scores.device)
+        N.check(self._lib.vs_merge_topk_dev(self._h, _ptr(cand_scores.contiguous()), _ptr(cand_rows.contiguous()),
+                                            G, B, k, _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
+        return out_scores, out_rows
+
+    # -- filter sweep / dedup -----------------------------------------------------------------
+    def filter_words(self) -> int:
+        return int(self._lib.vs_filter_words(self._h))
+
+    def filter_sweep(self, prompts, tau: float) -> np.ndarray:
+        """prompts [F, dim] float32 numpy -> uint32 bit mask [F, filter_words()]."""
+        a = np.ascontiguousarray(prompts, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[None]
+        out = np.zeros((a.shape[0], self.filter_words()), dtype=np.uint32)
+        N.check(self._lib.vs_filter_sweep_host(self._h, a.ctypes.data, a.shape[0], float(tau), out.ctypes.data))
+        return out
+
+    def filter_sweep_dev(self, prompts, tau: float, out_bits=None, stream=None):
+        import torch
+        F = prompts.shape[0]
+        if out_bits is None:
+            out_bits = torch.zeros((F, self.filter_words()), dtype=torch.int32, device=prompts.device)
+        st = stream if stream is not None else torch.cuda.current_stream(prompts.device)
+        N.check(self._lib.vs_filter_sweep_dev(self._h, _ptr(prompts.contiguous()), F, float(tau), _ptr(out_bits),
+                                              _stream_ptr(st)))
+        return out_bits
+
+    def dedup(self, tau: float, row_lo: int = 0, row_hi: Optional[int] = None, capacity: int = 1 << 20):
+        """All pairs (i<j) with cos >= tau for i in [row_lo,row_hi): (i, j, score) sorted by (i,j)."""
+        if row_hi is None:
+            row_hi = len(self)
+        while True:
+            oi = np.empty(capacity, dtype=np.int64)
+            oj = np.empty(capacity, dtype=np.int64)
+            os_ = np.empty(capacity, dtype=np.float32)
+            cnt = C.c_int64(0)
+            rc = self._lib.vs_dedup_host(self._h, int(row_lo), int(row_hi), float(tau), capacity,
+                                         oi.ctypes.data, oj.ctypes.data, os_.ctypes.data, C.byref(cnt))
+            if rc == N.VS_ERR_OVERFLOW:
+                capacity = int(cnt.value) + 1024
+                continue
+            N.check(rc)
+            m = int(cnt.value)
+            order = np.lexsort((oj[:m], oi[:m]))
+            return oi[:m][order], oj[:m][order], os_[:m][order]
+
+    def dedup_dev(self, tau: float, row_lo: int, row_hi: int, out_i, out_j, out_score, out_count, stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(out_i.device)
+        N.check(self._lib.vs_dedup_dev(self._h, int(row_lo), int(row_hi), float(tau), out_i.numel(), _ptr(out_i),
+                                       _ptr(out_j), _ptr(out_score), _ptr(out_count), _stream_ptr(st)))

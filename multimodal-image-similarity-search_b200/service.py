@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference's service functions that sit directly on the hot path.
+
+Same names, argument meaning and error behaviour as ``/root/reference/backend/app/main.py``
+(``search_similar`` :748-805, ``search_by_text`` :807-827, ``search_multimodal`` :829-867, the
+filter-application pass :201-222, the duplicate check of ``process_image`` :627-640), so the
+parity tests read like tests of the reference.  The CLIP encoder is NOT part of this package
+(north_star keeps it on the reference's PyTorch model): it is injected as a callable with the
+signature of ``generate_clip_embedding`` (backend/app/utils.py:59-102).
+"""
+from __future__ import annotations
+
+import json
+import logging
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+logger = logging.getLogger("mmiss_b200")
+
+Encoder = Callable[..., Dict[str, np.ndarray]]   # (image=None, text=None) -> {"image": [1,D], "text": [1,D]}
+
+
+def similarity_from_distance(distances: Sequence[float], legacy: bool = False) -> List[float]:
+    """``1 - d/2`` (backend/app/main.py:782) or the legacy ``1 - d`` (app.py:326)."""
+    if legacy:
+        return [1.0 - distance for distance in distances]
+    return [1 - (distance / 2) for distance in distances]
+
+
+def apply_filters(results: List[Dict[str, Any]], filters: Optional[Sequence[str]]) -> List[Dict[str, Any]]:
+    """The filter-application pass shared by the three search routes
+    (backend/app/main.py:201-222 == :257-278 == :319-340): a *post*-filter over ranked results."""
+    if not filters:
+        return results
+    filtered_results = []
+    for r in results:
+        filter_results = {}
+        if "filter_results_json" in r:
+            try:
+                filter_results = json.loads(r["filter_results_json"])
+            except (json.JSONDecodeError, TypeError):
+                logger.warning("Error parsing filter_results_json for image %s", r.get("id"))
+        if all(filter_results.get(f, "").lower().strip() == "yes" for f in filters):
+            filtered_results.append(r)
+    return filtered_results
+
+
+class SearchService:
+    """``collection`` is a :class:`mmiss_b200.Collection` (or anything chromadb-shaped)."""
+
+    def __init__(self, collection, encoder: Optional[Encoder] = None, legacy_scores: bool = False):
+        self.collection = collection
+        self.encoder = encoder
+        self.legacy_scores = legacy_scores
+
+    # -- backend/app/main.py:748-805 -------------------------------------------------------
+    def search_similar(self, embedding: np.ndarray, limit: int = 10) -> List[Dict]:
+        try:
+            actual_limit = 1000 if limit <= 0 else limit          # main.py:757 ("All" option)
+            results = self.collection.query(
+                query_embeddings=[np.asarray(embedding).tolist()],
+                n_results=actual_limit,
+                include=["metadatas", "distances"],
+            )
+            return self._assemble(results)
+        except Exception as e:  # the reference swallows and returns [] (main.py:803-805)
+            logger.error("Error searching for similar images: %s", e)
+            return []
+
+    def _assemble(self, results) -> List[Dict]:
+        """Result assembly of search_similar (main.py:767-801)."""
+        if not results or "ids" not in results or not results["ids"]:
+            return []
+        result_ids = results["ids"][0]
+        result_metadatas = results["metadatas"][0]
+        result_distances = results["distances"][0]
+        similarities = similarity_from_distance(result_distances, self.legacy_scores)
+        similar_images = []
+        for i, img_id in enumerate(result_ids):
+            result_metadata = (result_metadatas[i] or {}).copy()
+            result_metadata["similarity_score"] = similarities[i]
+            if "url" not in result_metadata:
+                result_metadata["url"] = f"/static/processed/{img_id}.png"
+            if "thumbnail_url" not in result_metadata:
+                result_metadata["thumbnail_url"] = f"/static/processed/{img_id}.png"
+            similar_images.append(result_metadata)
+        return similar_images
+
+    # -- backend/app/main.py:807-827 -------------------------------------------------------
+    def search_by_text(self, query_text: str, limit: int = 10) -> List[Dict]:
+        try:
+            text_embedding = self.encoder(text=query_text)["text"][0]
+            return self.search_similar(embedding=text_embedding, limit=limit)
+        except Exception as e:
+            logger.error("Error in text search: %s", e)
+            return []
+
+    def search_by_image(self, image, limit: int = 10) -> List[Dict]:
+        """Body of the /api/search/image route (backend/app/main.py:193-199)."""
+        try:
+            image_embedding = self.encoder(image=image)["image"][0]
+            return self.search_similar(embedding=image_embedding, limit=limit)
+        except Exception as e:
+            logger.error("Error in image search: %s", e)
+            return []
+
+    # -- backend/app/main.py:829-867 -------------------------------------------------------
+    def search_multimodal(self, image, query_text: str, weight_image: float = 0.5, limit: int = 10) -> List[Dict]:
+        try:
+            image_embedding = self.encoder(image=image)["image"][0]
+            text_embedding = self.encoder(text=query_text)["text"][0]
+            # blend (main.py:850-860) + query run on the device in one call
+            actual_limit = 1000 if limit <= 0 else limit
+            results = self.collection.query_multimodal(
+                image_embeddings=[np.asarray(image_embedding).tolist()],
+                text_embeddings=[np.asarray(text_embedding).tolist()],
+                weight_image=weight_image, n_results=actual_limit, include=["metadatas", "distances"])
+            return self._assemble(results)
+        except Exception as e:
+            logger.error("Error in multimodal search: %s", e)
+            return []
+
+    # -- the three routes' bodies: search + filter pass --------------------------------------
+    def route_search_text(self, query: str, filters: Optional[Sequence[str]] = None, limit: int = 10) -> Dict:
+        results = apply_filters(self.search_by_text(query, limit), filters)
+        return {"results": results}
+
+    def route_search_image(self, image, filters: Optional[Sequence[str]] = None, limit: int = 10) -> Dict:
+        return {"results": apply_filters(self.search_by_image(image, limit), filters)}
+
+    def route_search_multimodal(self, image, query: str, weight_image: float = 0.5,
+                                filters: Optional[Sequence[str]] = None, limit: int = 10) -> Dict:
+        return {"results": apply_filters(self.search_multimodal(image, query, weight_image, limit), filters)}
+
+    # -- duplicate check + ingest: process_image (backend/app/main.py:627-640, 686-744) ------------
+    def add_embedding(self, image_id: str, embedding: np.ndarray, metadata: Dict[str, Any],
+                      description: Optional[str] = None) -> Tuple[Dict[str, Any], bool]:
+        """Returns ``(metadata, is_new)``; an id that already exists returns the stored metadata and
+        ``False`` (the route turns that into HTTP 409, main.py:157-168)."""
+        existing_check = self.collection.get(ids=[image_id], include=["metadatas"])
+        if existing_check and existing_check["ids"]:
+            metadata_idx = existing_check["ids"].index(image_id)
+            return existing_check["metadatas"][metadata_idx], False
+        self.collection.add(ids=[image_id], embeddings=[np.asarray(embedding).tolist()], metadatas=[metadata],
+                            documents=[description])
+        return metadata, True
