@@ -90,6 +90,9 @@ struct vs_index {
   uint64_t* mask = nullptr;   // lazily allocated [cap][4]
   bool any_mask = false;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
   std::mutex mu;
   // scratch
   DevBuf d_q, d_out_s, d_out_r, d_part_s, d_part_r, d_tickets, d_scores, d_select, d_tensor, d_stage, d_misc;
@@ -191,6 +194,14 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
                      int64_t* out_r, cudaStream_t st) {
   if (B <= 0) return VS_OK;
   if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
+  // the scratch buffers (partial lists, tickets, select state) are shared by all queries of this
+  // index: serialise against the stream that used them last
+  if (ix->last_stream_valid && ix->last_stream != st) {
+    CU(cudaEventRecord(ix->ev, ix->last_stream));
+    CU(cudaStreamWaitEvent(st, ix->ev, 0));
+  }
+  ix->last_stream = st;
+  ix->last_stream_valid = true;
   if (ix->n == 0) {
     // empty collection: all slots empty
     CU(vs::launch_fill_empty(out_s, out_r, (int64_t)B * k, st));
@@ -313,6 +324,7 @@ int vs_create(int device, int dim, int dtype, int64_t capacity_rows, vs_index_t*
   ix->ld = pitch_elems(dim, ix->esize);
   ix->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete ix;
     return fail(VS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -341,6 +353,7 @@ int vs_destroy(vs_index_t* ix) {
   for (DevBuf* b : bufs) b->release();
   ix->h_in.release();
   ix->h_out.release();
+  if (ix->ev) cudaEventDestroy(ix->ev);
   cudaStreamDestroy(ix->stream);
   delete ix;
   return VS_OK;
@@ -373,6 +386,11 @@ int vs_add_dev(vs_index_t* ix, const float* rows_dev, int64_t n, int64_t* first_
   char* dst = (char*)ix->rows + (size_t)ix->n * ix->ld * ix->esize;
   CU(vs::launch_ingest(rows_dev, n, ix->dim, ix->dtype, dst, ix->ld, ix->inv + ix->n, st));
   if (ix->mask) CU(cudaMemsetAsync(ix->mask + (size_t)ix->n * vs::kMaskWords, 0, (size_t)n * vs::kMaskWords * 8, st));
+  if (st != ix->stream) {
+    // later work on the index's own stream (host-buffer queries) must see these rows
+    CU(cudaEventRecord(ix->ev, st));
+    CU(cudaStreamWaitEvent(ix->stream, ix->ev, 0));
+  }
   ix->n += n;
   return VS_OK;
 }

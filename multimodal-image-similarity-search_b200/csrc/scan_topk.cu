@@ -23,14 +23,12 @@
 
 namespace vs {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 220 * 1024;
 
-// rows per consumer warp per tile, chosen so a stage is <= 32 KB
-__host__ __device__ constexpr int rows_per_warp(int cpl) {
-  return cpl <= 1 ? 8 : cpl <= 2 ? 4 : cpl <= 4 ? 2 : 1;
+// rows per consumer warp per tile, chosen so a stage (W warps x U rows x pitch) is <= 32 KB
+__host__ __device__ constexpr int rows_per_warp(int cpl, int w) {
+  return (cpl <= 1 ? 64 : cpl <= 2 ? 32 : cpl <= 4 ? 16 : 8) / w > 0 ? (cpl <= 1 ? 64 : cpl <= 2 ? 32 : cpl <= 4 ? 16 : 8) / w : 1;
 }
 
 struct ScanKernelParams {
@@ -92,10 +90,11 @@ __device__ __forceinline__ bool mask_ok(const uint64_t* mask, uint32_t row, cons
 }
 
 // M == 0: materialise scores (large-k path) instead of keeping lists.
-template <typename T, int CPL, int M>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanKernelParams p) {
+template <typename T, int CPL, int M, int W, bool FULL>
+__global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKernelParams p) {
+  constexpr int kConsumerWarps = W;
   constexpr int EPC = Elem<T>::kPerChunk;
-  constexpr int U = rows_per_warp(CPL);
+  constexpr int U = rows_per_warp(CPL, W);
   constexpr int R = kConsumerWarps * U;
   constexpr int ML = M > 0 ? M : 1;
 
@@ -178,16 +177,28 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanKe
       const int st = it % p.stages;
       mbar_wait(&full[st], (it / p.stages) & 1);
       const uint8_t* tile = s_rows + (size_t)st * p.stage_stride + (size_t)(warp * U) * p.ld_bytes;
-      float acc[U];
+      // all LDS.128 of the warp's U rows are issued before any FMA (U*CPL loads in flight);
+      // FULL = every lane owns a valid chunk in every pass, so the loads are unpredicated
+      uint4 v[U][CPL];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint4* rp = reinterpret_cast<const uint4*>(tile + (size_t)u * p.ld_bytes);
-        float a = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           const int ch = c * 32 + lane;
-          if (ch < chunks) a += Elem<T>::dot(rp[ch], q[c]);
+          if (FULL || ch < chunks) v[u][c] = rp[ch];
+          else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
         }
+      }
+      float acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float part[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) part[c] = Elem<T>::dot(v[u][c], q[c]);   // U*CPL independent chains
+        float a = part[0];
+#pragma unroll
+        for (int c = 1; c < CPL; ++c) a += part[c];
         acc[u] = a;
       }
       float inv[U];
@@ -296,15 +307,20 @@ static int cpl_for(int64_t ld_bytes) {
   return -1;
 }
 
+// consumer warps per CTA, from the B200 A/B run (profiles/r01_scan_ab.md): bf16 rows carry twice the
+// FMA work per byte and run best with 8 warps x 4 rows in flight; f32 prefers 16 warps.
+static int scan_warps(int dtype) { return dtype == 0 ? 16 : 8; }
+
 int scan_rows_per_tile(int dtype, int64_t ld_bytes) {
-  (void)dtype;
   const int cpl = cpl_for(ld_bytes);
-  return cpl < 0 ? -1 : kConsumerWarps * rows_per_warp(cpl);
+  return cpl < 0 ? -1 : scan_warps(dtype) * rows_per_warp(cpl, scan_warps(dtype));
 }
 
-template <typename T, int CPL, int M>
+template <typename T, int CPL, int M, int W, bool FULL>
 static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) {
-  constexpr int U = rows_per_warp(CPL);
+  constexpr int kConsumerWarps = W;
+  constexpr int kScanThreads = (W + 1) * 32;
+  constexpr int U = rows_per_warp(CPL, W);
   constexpr int R = kConsumerWarps * U;
   constexpr int ML = M > 0 ? M : 1;
   ScanKernelParams p;
@@ -337,7 +353,7 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   if (stages < 2) return cudaErrorInvalidValue;
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + fixed;
-  auto kern = scan_topk_kernel<T, CPL, M>;
+  auto kern = scan_topk_kernel<T, CPL, M, W, FULL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int gx = a.grid_x > 0 ? a.grid_x : sm_count;
@@ -349,12 +365,18 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+template <typename T, int CPL, int W, bool FULL>
+static cudaError_t launch_mw(const ScanArgs& a, int sm_count, cudaStream_t st) {
+  if (a.scores_full) return launch_one<T, CPL, 0, W, FULL>(a, sm_count, st);
+  if (a.k <= 32) return launch_one<T, CPL, 1, W, FULL>(a, sm_count, st);
+  if (a.k <= 128) return launch_one<T, CPL, 4, W, FULL>(a, sm_count, st);
+  return cudaErrorInvalidValue;
+}
 template <typename T, int CPL>
 static cudaError_t launch_m(const ScanArgs& a, int sm_count, cudaStream_t st) {
-  if (a.scores_full) return launch_one<T, CPL, 0>(a, sm_count, st);
-  if (a.k <= 32) return launch_one<T, CPL, 1>(a, sm_count, st);
-  if (a.k <= 128) return launch_one<T, CPL, 4>(a, sm_count, st);
-  return cudaErrorInvalidValue;
+  const bool full = (a.ld_bytes / 16) == CPL * 32;
+  constexpr int W = sizeof(T) == 4 ? 16 : 8;
+  return full ? launch_mw<T, CPL, W, true>(a, sm_count, st) : launch_mw<T, CPL, W, false>(a, sm_count, st);
 }
 
 template <typename T>

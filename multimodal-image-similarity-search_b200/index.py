@@ -34,10 +34,17 @@ def _ptr(t) -> int:
     return 0 if t is None else int(t.data_ptr())
 
 
+_CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the C ABI reserves NULL for "the index's own stream"
+
+
 def _stream_ptr(stream) -> int:
+    """torch stream / raw handle -> cudaStream_t value for the C ABI.  torch's default stream
+    has handle 0, which the ABI would read as "use the index's own stream"; pass the explicit
+    legacy-default-stream handle instead so kernels really run on the caller's stream."""
     if stream is None:
         return 0
-    return int(getattr(stream, "cuda_stream", stream))
+    h = int(getattr(stream, "cuda_stream", stream))
+    return h if h != 0 else _CUDA_STREAM_LEGACY
 
 
 class DeviceIndex:
