@@ -129,7 +129,7 @@ int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_
 /* ---- filter sweep (BASELINE config 4; CLIP-side analogue of process_filter_on_all_images,
  *      backend/app/main.py:939-1056): prompts [F, dim] float32 (host or device) -> bit mask
  *      out_bits[F][words_per_filter] (uint32, bit n%32 of word n/32 set <=> cos >= tau),
- *      words_per_filter = ceil(count/32) rounded up to a multiple of 4.  tcgen05, bf16 storage. */
+ *      words_per_filter = vs_filter_words() = 8 * ceil(count/256).  tcgen05, bf16 storage. */
 int64_t vs_filter_words(const vs_index_t* ix);
 int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float tau,
                         uint32_t* out_bits_dev, void* stream);

@@ -137,13 +137,13 @@ int grow(vs_index* ix, int64_t need_rows) {
     return fail(VS_ERR_OOM, "cudaMalloc(%zu) for %lld rows failed: %s", (size_t)ncap * row_bytes, (long long)ncap,
                 cudaGetErrorString(e));
   }
-  e = cudaMalloc((void**)&ninv, ((size_t)ncap + 64) * sizeof(float));
+  e = cudaMalloc((void**)&ninv, ((size_t)ncap + 512) * sizeof(float));
   if (e != cudaSuccess) {
     cudaGetLastError();
     cudaFree(nrows);
     return fail(VS_ERR_OOM, "cudaMalloc inverse norms failed: %s", cudaGetErrorString(e));
   }
-  CU(cudaMemsetAsync(ninv, 0, ((size_t)ncap + 64) * sizeof(float), ix->stream));
+  CU(cudaMemsetAsync(ninv, 0, ((size_t)ncap + 512) * sizeof(float), ix->stream));
   uint64_t* nmask = nullptr;
   if (ix->mask) {
     e = cudaMalloc((void**)&nmask, (size_t)ncap * vs::kMaskWords * 8);
@@ -221,10 +221,11 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
   }
   int path = mode;
   if (path == VS_Q_AUTO)
-    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxFusedK && vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+            vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
   if (path == VS_Q_TENSOR) {
     if (ix->dtype != VS_BF16) return fail(VS_ERR_UNSUPPORTED, "tensor path needs bf16 storage");
-    if (k > vs::kMaxFusedK) return fail(VS_ERR_UNSUPPORTED, "tensor path supports k <= %d", vs::kMaxFusedK);
+    if (k > vs::kMaxTensorK) return fail(VS_ERR_UNSUPPORTED, "tensor path supports k <= %d", vs::kMaxTensorK);
     if (!vs::tensor_path_available()) return fail(VS_ERR_UNSUPPORTED, "tensor path not built");
     vs::TensorArgs ta;
     ta.rows = ix->rows;
@@ -597,8 +598,7 @@ int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_
 
 int64_t vs_filter_words(const vs_index_t* ix) {
   if (!ix) return 0;
-  const int64_t w = (ix->n + 31) / 32;
-  return (w + 3) / 4 * 4;
+  return (ix->n + 255) / 256 * 8;   // whole 256-row tiles: the sweep writes full tiles
 }
 
 int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float tau, uint32_t* out_bits_dev, void* stream) {

@@ -6,7 +6,8 @@
 namespace vs {
 
 constexpr int kMaskWords = 4;
-constexpr int kMaxFusedK = 128;   // register-list top-k limit of the fused kernels
+constexpr int kMaxFusedK = 128;   // register-list top-k limit of the fused scan kernel
+constexpr int kMaxTensorK = 32;   // per-thread register list limit of the tcgen05 top-k epilogue
 constexpr int kMaxK = 1024;
 
 void count_launch(int n = 1);
@@ -53,6 +54,9 @@ int scan_rows_per_tile(int dtype, int64_t ld_bytes);
 // [G][B][k] candidates (global rows, <0 empty) -> [B][k]
 cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
                          cudaStream_t st);
+// general form: candidates [G][Bstride][kin] -> [B][kout]
+cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
+                            float* out_s, int64_t* out_r, cudaStream_t st);
 // exact top-k (k <= 1024) of materialised scores [B][n] -> [B][k]; workspace: see select_workspace_bytes
 size_t select_workspace_bytes(int B);
 cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, void* workspace,

@@ -171,44 +171,45 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P) {
   __syncthreads();
 }
 
+// candidates: [G][Bstride][kin]; output [B][kout] (kout <= kin)
 __global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ cr, int G,
-                                                     int B, int k, int P, float* __restrict__ out_s,
+                                                     int Bstride, int kin, int kout, int P, float* __restrict__ out_s,
                                                      int64_t* __restrict__ out_r) {
   extern __shared__ __align__(16) uint64_t keys[];
   const int b = blockIdx.x;
-  const int C = G * k;
+  const int C = G * kin;
   for (int c = threadIdx.x; c < P; c += blockDim.x) {
     uint64_t key = 0;
     if (c < C) {
-      const int g = c / k, e = c - g * k;
-      const size_t src = ((size_t)g * B + b) * k + e;
+      const int g = c / kin, e = c - g * kin;
+      const size_t src = ((size_t)g * Bstride + b) * kin + e;
       const float s = cs[src];
       if (cr[src] >= 0 && s == s) key = ((uint64_t)score_key(s) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)c);
     }
     keys[c] = key;
   }
   bitonic_sort_desc(keys, P);
-  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+  for (int e = threadIdx.x; e < kout; e += blockDim.x) {
     const uint64_t key = e < P ? keys[e] : 0;
     float s = VS_NEG_INF;
     int64_t r = -1;
     if (key != 0) {
       const int c = (int)(0xFFFFFFFFu - (uint32_t)key);
-      const int g = c / k, ee = c - g * k;
-      const size_t src = ((size_t)g * B + b) * k + ee;
+      const int g = c / kin, ee = c - g * kin;
+      const size_t src = ((size_t)g * Bstride + b) * kin + ee;
       s = cs[src];
       r = cr[src];
     }
-    out_s[(size_t)b * k + e] = s;
-    out_r[(size_t)b * k + e] = r;
+    out_s[(size_t)b * kout + e] = s;
+    out_r[(size_t)b * kout + e] = r;
   }
 }
 
-cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
-                         cudaStream_t st) {
-  if (G <= 0 || B <= 0 || k <= 0) return cudaErrorInvalidValue;
+cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
+                            float* out_s, int64_t* out_r, cudaStream_t st) {
+  if (G <= 0 || B <= 0 || kin <= 0 || kout <= 0 || kout > kin || Bstride < B) return cudaErrorInvalidValue;
   int P = 2;
-  while (P < G * k) P <<= 1;
+  while (P < G * kin) P <<= 1;
   if (P > 16384) return cudaErrorInvalidValue;
   const size_t smem = (size_t)P * 8;
   static bool attr_set = false;
@@ -218,9 +219,14 @@ cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k
     attr_set = true;
   }
   const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
-  merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, B, k, P, out_s, out_r);
+  merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, Bstride, kin, kout, P, out_s, out_r);
   count_launch();
   return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
+                         cudaStream_t st) {
+  return launch_merge_ex(cs, cr, G, B, B, k, k, out_s, out_r, st);
 }
 
 // ------------------------------------------------------------------------------------------
