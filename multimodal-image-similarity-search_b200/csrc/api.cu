@@ -236,7 +236,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     ta.ld_elems = ix->ld;
     ta.n_rows = ix->n;
     ta.row_base = ix->row_base;
-    CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B, ix->dim, k, ix->sm_count)));
+    CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B, ix->dim, k, ix->sm_count, ix->n)));
     CU(vs::launch_tensor_topk(ta, q_dev, B, k, ix->d_tensor.p, out_s, out_r, ix->sm_count, st));
     ix->last_path = VS_Q_TENSOR;
     return VS_OK;
@@ -618,7 +618,7 @@ int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float t
   ta.ld_elems = ix->ld;
   ta.n_rows = ix->n;
   ta.row_base = ix->row_base;
-  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(F, ix->dim, 1, ix->sm_count)));
+  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(F, ix->dim, 1, ix->sm_count, ix->n)));
   CU(vs::launch_tensor_filter(ta, prompts_dev, F, tau, ix->d_tensor.p, out_bits_dev, vs_filter_words(ix), ix->sm_count,
                               pick_stream(ix, stream)));
   return VS_OK;
@@ -666,7 +666,7 @@ int vs_dedup_dev(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int6
   ta.ld_elems = ix->ld;
   ta.n_rows = ix->n;
   ta.row_base = ix->row_base;
-  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(128, ix->dim, 1, ix->sm_count)));
+  CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(128, ix->dim, 1, ix->sm_count, ix->n)));
   CU(vs::launch_tensor_dedup(ta, row_lo, row_hi, tau, cap, out_i_dev, out_j_dev, out_score_dev, out_count_dev,
                              ix->d_tensor.p, ix->sm_count, st));
   return VS_OK;

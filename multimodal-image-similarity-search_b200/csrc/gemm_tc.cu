@@ -8,11 +8,13 @@
 //   A = a block of 128 "query-side" vectors (queries / prompts / a block of corpus rows), bf16,
 //       RESIDENT in shared memory for the whole work item (loaded once by TMA, 128B swizzle),
 //   B = corpus rows, streamed from HBM in tiles of BN rows x 64 k-elements by TMA into a ring of
-//       stages (the corpus is read once per A block; CTAs that share a corpus slice run in
-//       lock-step so the re-reads are L2 hits),
+//       stages.  The C CTAs of a thread-block CLUSTER own C different A blocks and share ONE
+//       corpus stream: each CTA fetches 1/C of every B tile and TMA-multicasts it into the
+//       shared memory of all C CTAs, so a corpus byte crosses L2->SM once per cluster instead of
+//       once per A block (without this the kernel is L2-bandwidth bound: 64 B/cycle/SM),
 //   D = fp32 accumulators in TMEM: lane = query, column = corpus row, 512/BN buffers so the MMA
 //       of tile t+1 overlaps the epilogue of tile t.
-// Roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread), warps 2..5 =
+// Roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread), warps 2..9 =
 // epilogue (tcgen05.ld 32x32b: each thread owns ONE query and sees that query's scores against
 // 32 consecutive rows per load -> a private register top-k list, no cross-thread traffic).
 // Epilogue arithmetic: score = acc * inv_norm[row] (queries are L2-normalised then rounded to
@@ -21,6 +23,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 
 #include "common.cuh"
@@ -30,7 +33,7 @@ namespace vs {
 
 constexpr int kTcM = 128;          // A rows per block (UMMA M)
 constexpr int kTcKB = 64;          // k elements per stage (= 128 B = one swizzle span)
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;      // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTcMaxStages = 8;
 constexpr int kTcSmemMax = 232448; // 227 KB
 
@@ -46,19 +49,23 @@ struct TcParams {
   uint32_t n_tiles;        // ceil(n_rows / BN)
   int kb_count;            // ceil(dim / 64)
   int stages;
-  int n_chunks;            // A blocks
-  int n_slices;            // corpus slices (top-k / filter)
+  int n_slices;            // corpus slices (top-k / filter); one cluster per slice per pass
   int tiles_per_slice;
-  int n_items;
+  int n_items;             // work items per cluster sequence
+  int prefetch;            // B stages to prefetch into L2 ahead of the smem ring
+  int debug_noepi;         // VS_TC_DEBUG_NOEPI=1: epilogue only hands the accumulator back (profiling aid)
+  unsigned long long* dbg; // VS_TC_DEBUG_COUNT=1: [groups, slow-path entries, lanes that hit, inserts]
+  const float* gmin;       // [ceil(n_rows/32)] (1 - 2^-20) * min row norm of each 32-row group (+inf if empty)
   // top-k
-  float* part_s;           // [n_slices][Bp][KL]
+  uint32_t* gbound;        // [Bp] orderable key of the best known lower bound on each query's k-th score
+  float* part_s;           // [n_slices][2][Bp][KL]  (2 = the two epilogue halves)
   int64_t* part_r;
-  int Bp;
+  int Bp;                  // C * 128
   // filter
   uint32_t* out_bits;
   int64_t words_per_filter;
   float tau;
-  int F;
+  int F;                   // valid A rows in this launch (rows >= F are padding)
   // dedup
   int64_t a_row_lo;        // first corpus row of A block 0 (128-aligned)
   int64_t a_row_min;       // caller's row_lo: rows below it are not reported
@@ -71,8 +78,17 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers: TMA tensor loads, tcgen05 (alloc / mma / commit / ld / fences)
+// PTX wrappers: clusters, TMA tensor loads, tcgen05 (alloc / mma / commit / ld / fences)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
                                             uint64_t policy) {
   asm volatile(
@@ -81,6 +97,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
       "l"(policy)
       : "memory");
+}
+// same box delivered to the same CTA-relative smem offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0),
+      "r"(c1), "l"(policy)
+      : "memory");
+}
+// pull a box into L2 only (no smem, no barrier): hides HBM latency behind the shallow smem ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -110,6 +142,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// ... and on the same barrier of every CTA of the cluster in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 // 32 lanes x 32 consecutive columns: thread i of the warp receives lane (base+i), columns c..c+31
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -179,15 +218,17 @@ __device__ __forceinline__ bool tc_mask_ok(const uint64_t* mask, uint32_t row, c
 }
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  C = cluster size (CTAs sharing one corpus stream, one A block each)
 // ------------------------------------------------------------------------------------------
-template <int MODE, int BN, int KL>
+template <int MODE, int BN, int KL, int C>
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   constexpr int ACC = 512 / BN;              // accumulator buffers in TMEM
   constexpr uint32_t kStageBytes = BN * 128; // BN rows x 64 bf16
+  constexpr uint32_t kPartRows = BN / C;     // rows of each B tile this CTA fetches (and multicasts)
   constexpr uint32_t kABlockBytes = kTcM * 128;
   constexpr uint32_t kIdesc = make_idesc(kTcM, BN);
+  constexpr uint16_t kMask = (uint16_t)((1u << C) - 1u);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 128B swizzle: 1024-B aligned
@@ -203,15 +244,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = C > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / C;
+  const int n_clusters = gridDim.x / C;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], C);   // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);   // one arrival per epilogue warp
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -223,21 +267,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
   tc_fence_before();
-  __syncthreads();
+  if (C > 1) cluster_sync_all(); else __syncthreads();   // barriers of every CTA initialised before remote arrivals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  // work item -> (A block, tile range); identical sequence in every role
-  auto item_range = [&](int w, int& chunk, uint32_t& t0, uint32_t& t1) {
+  // work item (one per cluster) -> this CTA's A block + the cluster's tile range
+  auto item_range = [&](int w, int& ablock, uint32_t& t0, uint32_t& t1) {
     if (MODE == kModeDedup) {
-      chunk = w;
-      const uint32_t a_row0 = (uint32_t)p.a_row_lo + (uint32_t)w * kTcM;
+      ablock = w * C + (int)rank;
+      const uint32_t a_row0 = (uint32_t)p.a_row_lo + (uint32_t)(w * C) * kTcM;   // cluster's first row
       t0 = a_row0 / BN;       // only columns j > i can pair with row i
       t1 = p.n_tiles;
     } else {
-      chunk = w % p.n_chunks;
-      const int slice = w / p.n_chunks;
-      t0 = (uint32_t)slice * p.tiles_per_slice;
+      ablock = (int)rank;
+      t0 = (uint32_t)w * p.tiles_per_slice;
       t1 = min(t0 + (uint32_t)p.tiles_per_slice, p.n_tiles);
     }
   };
@@ -248,23 +291,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint64_t pol_stream = policy_evict_first();
       const uint64_t pol_keep = policy_evict_last();
       uint32_t it = 0, n_item = 0;
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++n_item) {
-        int chunk;
+      for (int w = cluster_id; w < p.n_items; w += n_clusters, ++n_item) {
+        int ablock;
         uint32_t t0, t1;
-        item_range(w, chunk, t0, t1);
+        item_range(w, ablock, t0, t1);
         // A block: resident for the whole item
         if (n_item > 0) mbar_wait(a_empty, (n_item - 1) & 1);
         mbar_expect_tx(a_full, (uint32_t)p.kb_count * kABlockBytes);
-        const int a_row = MODE == kModeDedup ? (int)(p.a_row_lo + (int64_t)chunk * kTcM) : chunk * kTcM;
+        const int a_row = MODE == kModeDedup ? (int)(p.a_row_lo + (int64_t)ablock * kTcM) : ablock * kTcM;
         for (int kb = 0; kb < p.kb_count; ++kb)
           tma_load_2d(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+        // L2 prefetch runs `prefetch` stages ahead of the smem ring (this CTA's part of each box)
+        const uint32_t n_st = (t1 - t0) * (uint32_t)p.kb_count;
+        auto prefetch_stage = [&](uint32_t idx) {
+          if (idx < n_st) {
+            const uint32_t pt = t0 + idx / (uint32_t)p.kb_count;
+            const int pkb = (int)(idx % (uint32_t)p.kb_count);
+            tma_prefetch_2d(&tmB, pkb * kTcKB, (int)(pt * BN + rank * kPartRows));
+          }
+        };
+        for (uint32_t i = 0; i < (uint32_t)p.prefetch; ++i) prefetch_stage(i);
+        uint32_t idx = 0;
         for (uint32_t t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+          for (int kb = 0; kb < p.kb_count; ++kb, ++it, ++idx) {
             const int st = it % p.stages;
             const uint32_t use = it / p.stages;
-            if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
-            mbar_expect_tx(&full[st], kStageBytes);
-            tma_load_2d(sB + (size_t)st * kStageBytes, &tmB, kb * kTcKB, (int)(t * BN), &full[st], pol_stream);
+            if (p.prefetch > 0) prefetch_stage(idx + (uint32_t)p.prefetch);
+            if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);   // all C CTAs have consumed this stage
+            mbar_expect_tx(&full[st], kStageBytes);              // the whole tile: C parts from C CTAs
+            uint8_t* dst = sB + (size_t)st * kStageBytes + (size_t)rank * kPartRows * 128;
+            const int row = (int)(t * BN + rank * kPartRows);
+            if (C > 1)
+              tma_load_2d_mc(dst, &tmB, kb * kTcKB, row, &full[st], kMask, pol_stream);
+            else
+              tma_load_2d(dst, &tmB, kb * kTcKB, row, &full[st], pol_stream);
           }
         }
       }
@@ -274,10 +334,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ================= MMA issuer ===============================================================
     if (lane == 0) {
       uint32_t it = 0, n_item = 0, tile_ctr = 0;
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++n_item) {
-        int chunk;
+      for (int w = cluster_id; w < p.n_items; w += n_clusters, ++n_item) {
+        int ablock;
         uint32_t t0, t1;
-        item_range(w, chunk, t0, t1);
+        item_range(w, ablock, t0, t1);
         mbar_wait(a_full, n_item & 1);
         tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
@@ -295,7 +355,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int k = 0; k < kTcKB / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance start address by 2 (16-B units)
               umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
-            umma_commit(&empty[st]);               // frees the stage when these MMAs have read it
+            // frees the stage (in every CTA of the cluster) when these MMAs have read it
+            if (C > 1) umma_commit_mc(&empty[st], kMask); else umma_commit(&empty[st]);
           }
           umma_commit(&tfull[acc]);                // accumulator ready for the epilogue
         }
@@ -304,32 +365,50 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps (2..5): TMEM lane quarter = warp % 4 ========================
+    // ================= epilogue warps (2..9): TMEM lane quarter = warp % 4 ==========================
+    // Two warps per lane quarter (one per scheduler pair) split the 32-column groups of every tile
+    // even/odd, so TMEM/global latencies of one overlap the list work of the other.  Each thread
+    // owns ONE query and keeps its own list; the two lists of a query are merged with the slices'.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;              // 0: even groups, 1: odd groups
     const int m_local = quarter * 32 + lane;       // A row (query) owned by this thread
     ThreadTopK<KL> top;
     uint32_t tile_ctr = 0;
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-      int chunk;
+    for (int w = cluster_id; w < p.n_items; w += n_clusters) {
+      int ablock;
       uint32_t t0, t1;
-      item_range(w, chunk, t0, t1);
+      item_range(w, ablock, t0, t1);
       if (MODE == kModeTopK) top.init();
-      const uint32_t a_global = (MODE == kModeDedup ? (uint32_t)p.a_row_lo : 0u) + (uint32_t)chunk * kTcM + m_local;
+      const uint32_t a_global = (MODE == kModeDedup ? (uint32_t)p.a_row_lo : 0u) + (uint32_t)ablock * kTcM + m_local;
       float inv_a = 1.f;
-      if (MODE == kModeDedup) inv_a = a_global < p.n_rows ? __ldg(p.inv_norm + a_global) : 0.f;
+      bool a_ok = true;
+      if (MODE == kModeDedup) {
+        a_ok = a_global < (uint32_t)p.a_row_hi && a_global >= (uint32_t)p.a_row_min;
+        inv_a = a_ok ? __ldg(p.inv_norm + a_global) : 0.f;
+      }
+      // top-k: a lower bound on this query's global k-th score, shared by all threads (slices,
+      // halves) that work on the same query through gbound[] (atomicMax on orderable keys).  A row
+      // scoring strictly below it cannot be in the global top-k.
+      uint32_t* gb_ptr = nullptr;
+      float published = VS_NEG_INF;
+      if (MODE == kModeTopK) gb_ptr = p.gbound + (size_t)ablock * kTcM + m_local;
       for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t acc = tile_ctr % ACC;
+        float gb = VS_NEG_INF;
+        if (MODE == kModeTopK && p.debug_noepi != 4) gb = key_score(*reinterpret_cast<volatile uint32_t*>(gb_ptr));
         mbar_wait(&tfull[acc], (tile_ctr / ACC) & 1);
         tc_fence_after();
         const uint32_t row0 = t * BN;
+        const int n_groups = p.debug_noepi == 1 ? 0 : BN / 32;   // debug_noepi: profiling aid (see TcParams)
 #pragma unroll 1
-        for (int g = 0; g < BN / 32; ++g) {
+        for (int g = half; g < n_groups; g += 2) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
           const uint32_t rg = row0 + g * 32;
-          float inv[32];
-          {
-            const float4* ip = reinterpret_cast<const float4*>(p.inv_norm + rg);   // padded past n_rows
+          const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
+          const float4* ip = reinterpret_cast<const float4*>(p.inv_norm + rg);   // padded past n_rows
+          if (MODE == kModeFilter) {
+            float inv[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 f = __ldg(ip + j);
@@ -338,39 +417,92 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               inv[4 * j + 2] = f.z;
               inv[4 * j + 3] = f.w;
             }
-          }
-          tmem_ld_wait();
-          const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
-          if (MODE == kModeTopK) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]) * inv[j];
-              if (s > top.threshold() && (uint32_t)j < nvalid) {
-                const uint32_t row = rg + j;
-                if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) top.insert(s, row);
-              }
-            }
-          } else if (MODE == kModeFilter) {
+            tmem_ld_wait();
             uint32_t bits = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]) * inv[j];
-              bits |= (s >= p.tau && (uint32_t)j < nvalid) ? (1u << j) : 0u;
-            }
-            const uint32_t f = (uint32_t)chunk * kTcM + m_local;
+            for (int j = 0; j < 32; ++j)
+              bits |= (__uint_as_float(v[j]) * inv[j] >= p.tau && (uint32_t)j < nvalid) ? (1u << j) : 0u;
+            const uint32_t f = (uint32_t)ablock * kTcM + m_local;
             if (f < (uint32_t)p.F) p.out_bits[(size_t)f * p.words_per_filter + rg / 32] = bits;
           } else {
+            // Fast reject on RAW accumulators: score_j = acc_j * inv_j <= max_j(acc_j) / min_j(norm_j).
+            // gmin = (1 - 2^-20) * min norm of the 32 rows, so `max acc <= bound * gmin` proves that no
+            // row of the group reaches `bound`; one max tree + one warp vote per 32 rows.  The exact
+            // arithmetic (acc * inv_norm, as the oracle) only runs in the rare slow path.
+            const float gmn = __ldg(p.gmin + (rg >> 5));
+            tmem_ld_wait();
+            float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]) * inv_a * inv[j];
-              const uint32_t row = rg + j;
-              if (s >= p.tau && (uint32_t)j < nvalid && a_global < row && a_global < (uint32_t)p.a_row_hi &&
-                  a_global >= (uint32_t)p.a_row_min) {
-                const unsigned long long slot = atomicAdd(p.out_count, 1ull);
-                if ((int64_t)slot < p.cap) {
-                  p.out_i[slot] = (int64_t)a_global + p.row_base;
-                  p.out_j[slot] = (int64_t)row + p.row_base;
-                  p.out_score[slot] = s;
+            for (int j = 2; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            bool hit;
+            if (MODE == kModeTopK) {
+              const float tb = fmaxf(top.threshold(), gb);
+              hit = tb > 0.f ? (m > tb * gmn) : (nvalid > 0);
+            } else {
+              hit = p.tau > 0.f ? (m * inv_a >= p.tau * gmn) : (nvalid > 0);
+            }
+            if (p.debug_noepi == 2) hit = false;
+            if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1ull);
+            if (p.debug_noepi != 3 && __any_sync(0xffffffffu, hit)) {
+              if (p.dbg) {
+                if (lane == 0) atomicAdd(p.dbg + 1, 1ull);
+                if (hit) atomicAdd(p.dbg + 2, 1ull);
+              }
+              // ---- slow path (compact on purpose: one insert site, no per-column code copies) ----
+              // exact scores + a per-lane bitmask of candidate columns, then candidates are pulled
+              // out in ascending column (= row) order with a select tree (no dynamic register index)
+              float sc[32];
+              uint32_t cm = 0;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 f = __ldg(ip + j4);
+                sc[4 * j4] = __uint_as_float(v[4 * j4]) * f.x;
+                sc[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
+                sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
+                sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
+              }
+              const float thr0 = top.threshold();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                bool c;
+                if (MODE == kModeTopK) {
+                  c = sc[j] > thr0 && sc[j] >= gb;
+                } else {
+                  sc[j] *= inv_a;
+                  c = sc[j] >= p.tau && a_ok && a_global < rg + j;
+                }
+                cm |= (c && (uint32_t)j < nvalid) ? (1u << j) : 0u;
+              }
+#pragma unroll 1
+              while (__any_sync(0xffffffffu, cm != 0u)) {
+                if (cm != 0u) {
+                  const int j = __ffs(cm) - 1;
+                  cm &= cm - 1u;
+                  // select tree: sc[j] without indexing registers dynamically
+                  float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) t16[i] = (j & 16) ? sc[i + 16] : sc[i];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) t8[i] = (j & 8) ? t16[i + 8] : t16[i];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[i + 4] : t8[i];
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) t2[i] = (j & 2) ? t4[i + 2] : t4[i];
+                  const float s = (j & 1) ? t2[1] : t2[0];
+                  const uint32_t row = rg + j;
+                  if (MODE == kModeTopK) {
+                    if (s > top.threshold()) {
+                      if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
+                      if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) top.insert(s, row);
+                    }
+                  } else {
+                    const unsigned long long slot = atomicAdd(p.out_count, 1ull);
+                    if ((int64_t)slot < p.cap) {
+                      p.out_i[slot] = (int64_t)a_global + p.row_base;
+                      p.out_j[slot] = (int64_t)row + p.row_base;
+                      p.out_score[slot] = s;
+                    }
+                  }
                 }
               }
             }
@@ -380,10 +512,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (MODE == kModeTopK && p.debug_noepi != 4 && top.threshold() > published) {
+          published = top.threshold();
+          atomicMax(gb_ptr, score_key(published));
+        }
       }
       if (MODE == kModeTopK) {
-        const int slice = w / p.n_chunks;
-        const size_t base = ((size_t)slice * p.Bp + (size_t)chunk * kTcM + m_local) * KL;
+        // partial lists: [slice][half][Bp][KL]
+        const size_t base = (((size_t)w * 2 + half) * p.Bp + (size_t)ablock * kTcM + m_local) * KL;
 #pragma unroll
         for (int j = 0; j < KL; ++j) {
           p.part_s[base + j] = top.s[j];
@@ -394,7 +530,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its smem or arrive on its barriers
+  if (C > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -405,10 +542,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // query preparation: normalise (f32), round to bf16, zero-pad to [Bp][Dp]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int B, int dim, int Bp, int Dp,
-                                                           __nv_bfloat16* __restrict__ out) {
+                                                           __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ gbound) {
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= Bp) return;
+  if (lane == 0 && gbound) gbound[b] = score_key(VS_NEG_INF);
   __nv_bfloat16* o = out + (size_t)b * Dp;
   if (b >= B) {
     for (int e = lane; e < Dp; e += 32) o[e] = __float2bfloat16_rn(0.f);
@@ -421,6 +559,20 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
   const float inv = 1.0f / (sqrtf(ss) + 1e-30f);
   for (int e = lane; e < Dp; e += 32) o[e] = __float2bfloat16_rn(e < dim ? s[e] * inv : 0.f);
+}
+
+// gmin[g] = (1 - 2^-20) * min over the valid rows of 32-row group g of the row norm 1/inv_norm
+// (+inf for a group with no valid row); see the fast-reject test in the epilogue.
+__global__ void __launch_bounds__(256) group_min_norm_kernel(const float* __restrict__ inv, uint32_t n_rows,
+                                                             uint32_t n_groups, float* __restrict__ gmin) {
+  const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n_groups) return;
+  const uint32_t row = g * 32 + (threadIdx.x & 31);
+  float nrm = __int_as_float(0x7f800000);
+  if (row < n_rows) nrm = 1.0f / __ldg(inv + row);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) nrm = fminf(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+  if ((threadIdx.x & 31) == 0) gmin[g] = nrm * (1.0f - 9.5367431640625e-07f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,12 +611,21 @@ static cudaError_t make_map(CUtensorMap* map, const void* base, uint64_t rows, u
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static int tc_block_n() {
-  static int bn = [] {
-    const char* e = getenv("VS_TC_BN");
-    return (e && atoi(e) == 128) ? 128 : 256;
-  }();
+  static int bn = env_int("VS_TC_BN", 256) == 128 ? 128 : 256;
   return bn;
+}
+// largest cluster size allowed (1, 2, 4 or 8); tuned on B200, see profiles/
+static int tc_max_cluster() {
+  static int c = [] {
+    const int v = env_int("VS_TC_CLUSTER", 8);
+    return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
+  }();
+  return c;
 }
 
 struct TcPlan {
@@ -490,27 +651,120 @@ static TcPlan plan_for(int dim) {
 }
 
 static int kl_for(int k) { return k <= 10 ? 10 : 32; }
+static int cluster_for(int chunks) {
+  int c = 1;
+  while (c * 2 <= chunks && c * 2 <= tc_max_cluster()) c *= 2;
+  return c;
+}
 
-size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count) {
+// workspace layout: [gmin f32 x groups][gbound u32 x Bp][queries bf16 Bp x Dp][partial lists]
+struct TcWorkspace {
+  float* gmin;
+  uint32_t* gbound;
+  __nv_bfloat16* q;
+  float* parts;
+  uint32_t n_groups;
+  size_t total;
+};
+static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_count, int64_t n_rows) {
   const TcPlan pl = plan_for(dim);
   const int Bp = (B + kTcM - 1) / kTcM * kTcM;
   const int KL = kl_for(k);
-  size_t q = (size_t)Bp * pl.Dp * 2;
-  q = (q + 255) & ~(size_t)255;
-  const size_t parts = (size_t)sm_count * Bp * KL * 12 + 512;
-  return q + parts;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  TcWorkspace w;
+  w.n_groups = (uint32_t)((n_rows + 255) / 256 * 8);   // whole 256-row tiles
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  w.gmin = reinterpret_cast<float*>(p + off);
+  off += up((size_t)w.n_groups * 4);
+  w.gbound = reinterpret_cast<uint32_t*>(p + off);
+  off += up((size_t)Bp * 4);
+  w.q = reinterpret_cast<__nv_bfloat16*>(p + off);
+  off += up((size_t)Bp * pl.Dp * 2);
+  w.parts = reinterpret_cast<float*>(p + off);
+  off += (size_t)2 * sm_count * 8 * kTcM * KL * 12 + 1024;   // <= sm_count slices x 2 halves x (8 x 128) queries
+  w.total = off;
+  return w;
+}
+size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count, int64_t n_rows) {
+  return carve_workspace(nullptr, B, dim, k, sm_count, n_rows).total;
+}
+static void launch_gmin(const TensorArgs& a, const TcWorkspace& w, cudaStream_t st) {
+  group_min_norm_kernel<<<(w.n_groups + 7) / 8, 256, 0, st>>>(a.inv_norm, (uint32_t)a.n_rows, w.n_groups, w.gmin);
+  count_launch();
+}
+static int tc_prefetch() {
+  static int v = env_int("VS_TC_PREFETCH", 0);   // measured on B200: no gain for top-k, a loss for the sweep
+  return v < 0 ? 0 : v > 64 ? 64 : v;
 }
 
-template <int MODE, int BN, int KL>
-static cudaError_t launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const TcPlan& pl, int grid,
-                             cudaStream_t st) {
-  auto kern = tc_kernel<MODE, BN, KL>;
+template <int MODE, int BN, int KL, int C>
+static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const TcPlan& pl,
+                               int n_clusters_wanted, cudaStream_t st) {
+  auto kern = tc_kernel<MODE, BN, KL, C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kTcThreads, pl.smem, st>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(n_clusters_wanted * C), 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
+
+// how many clusters of size C (with this kernel's smem) can be co-resident
+template <int MODE, int BN, int KL, int C>
+static int max_clusters(const TcPlan& pl, int sm_count) {
+  auto kern = tc_kernel<MODE, BN, KL, C>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
+    cudaGetLastError();
+    return sm_count / C;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(sm_count / C * C), 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count / C;
+  }
+  return n;
+}
+
+#define VS_TC_DISPATCH_C(FN, MODE, BN, KL, C, ...)            \
+  ((C) == 8   ? FN<MODE, BN, KL, 8>(__VA_ARGS__)              \
+   : (C) == 4 ? FN<MODE, BN, KL, 4>(__VA_ARGS__)              \
+   : (C) == 2 ? FN<MODE, BN, KL, 2>(__VA_ARGS__)              \
+              : FN<MODE, BN, KL, 1>(__VA_ARGS__))
+#define VS_TC_DISPATCH(FN, MODE, BN, KL, C, ...)                                    \
+  ((BN) == 256 ? ((KL) == 10 ? VS_TC_DISPATCH_C(FN, MODE, 256, 10, C, __VA_ARGS__)  \
+                             : VS_TC_DISPATCH_C(FN, MODE, 256, 32, C, __VA_ARGS__)) \
+               : ((KL) == 10 ? VS_TC_DISPATCH_C(FN, MODE, 128, 10, C, __VA_ARGS__)  \
+                             : VS_TC_DISPATCH_C(FN, MODE, 128, 32, C, __VA_ARGS__)))
+
+// filter / dedup epilogues keep no list: only the KL = 10 instantiation exists for them
+#define VS_TC_DISPATCH10(FN, MODE, BN, C, ...)                               \
+  ((BN) == 256 ? VS_TC_DISPATCH_C(FN, MODE, 256, 10, C, __VA_ARGS__)         \
+               : VS_TC_DISPATCH_C(FN, MODE, 128, 10, C, __VA_ARGS__))
 
 static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   memset(&p, 0, sizeof(p));
@@ -527,6 +781,17 @@ static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   p.n_tiles = (uint32_t)((a.n_rows + pl.BN - 1) / pl.BN);
   p.kb_count = pl.kb_count;
   p.stages = pl.stages;
+  p.prefetch = tc_prefetch();
+  static const int noepi = env_int("VS_TC_DEBUG_NOEPI", 0);
+  p.debug_noepi = noepi;
+}
+
+static void plan_slices(TcParams& p, int n_clusters) {
+  p.n_slices = n_clusters < (int)p.n_tiles ? n_clusters : (int)p.n_tiles;
+  if (p.n_slices < 1) p.n_slices = 1;
+  p.tiles_per_slice = (int)((p.n_tiles + p.n_slices - 1) / p.n_slices);
+  p.n_slices = (int)((p.n_tiles + p.tiles_per_slice - 1) / p.tiles_per_slice);
+  p.n_items = p.n_slices;
 }
 
 static bool dims_ok(const TensorArgs& a) { return a.dim >= 8 && a.dim % 8 == 0 && a.ld_elems % 8 == 0; }
@@ -534,48 +799,56 @@ static bool dims_ok(const TensorArgs& a) { return a.dim >= 8 && a.dim % 8 == 0 &
 cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k, void* workspace, float* out_s,
                                int64_t* out_r, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
-  if (!pl.ok || !dims_ok(a) || k > 32 || B <= 0) return cudaErrorNotSupported;
+  if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || B <= 0) return cudaErrorNotSupported;
   const int Bp = (B + kTcM - 1) / kTcM * kTcM;
   const int KL = kl_for(k);
-  __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
-  size_t qbytes = ((size_t)Bp * pl.Dp * 2 + 255) & ~(size_t)255;
-  float* part_s = reinterpret_cast<float*>(static_cast<char*>(workspace) + qbytes);
+  const TcWorkspace ws = carve_workspace(workspace, B, a.dim, k, sm_count, a.n_rows);
+  __nv_bfloat16* qb = ws.q;
+  float* part_s = ws.parts;
 
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb);
+  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb, ws.gbound);
   count_launch();
+  launch_gmin(a, ws, st);
 
   const int chunks_total = Bp / kTcM;
-  // process at most `sm_count` query chunks per launch (each chunk needs >= 1 CTA)
-  for (int c0 = 0; c0 < chunks_total; c0 += sm_count) {
-    const int nch = min(sm_count, chunks_total - c0);
+  for (int c0 = 0; c0 < chunks_total;) {
+    const int C = cluster_for(chunks_total - c0);
     TcParams p;
     fill_common(p, a, pl);
-    p.n_chunks = nch;
-    p.n_slices = max(1, min(sm_count / nch, (int)p.n_tiles));
-    p.tiles_per_slice = (int)((p.n_tiles + p.n_slices - 1) / p.n_slices);
-    p.n_slices = (int)((p.n_tiles + p.tiles_per_slice - 1) / p.tiles_per_slice);
-    p.n_items = p.n_chunks * p.n_slices;
-    p.Bp = nch * kTcM;
+    p.gmin = ws.gmin;
+    p.gbound = ws.gbound + (size_t)c0 * kTcM;
+    const int ncl = VS_TC_DISPATCH(max_clusters, kModeTopK, pl.BN, KL, C, pl, sm_count);
+    plan_slices(p, ncl);
+    p.Bp = C * kTcM;
     p.part_s = part_s;
-    p.part_r = reinterpret_cast<int64_t*>(part_s + (size_t)p.n_slices * p.Bp * KL + 64);
-    p.part_r = reinterpret_cast<int64_t*>(((uintptr_t)p.part_r + 15) & ~(uintptr_t)15);
+    p.part_r = reinterpret_cast<int64_t*>(((uintptr_t)(part_s + (size_t)2 * p.n_slices * p.Bp * KL) + 255) & ~(uintptr_t)255);
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)nch * kTcM, pl.Dp, pl.Dp, kTcM);
+    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN);
+    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
     if (e != cudaSuccess) return e;
-    const int grid = p.n_items;
-    if (pl.BN == 256)
-      e = KL == 10 ? launch_tc<kModeTopK, 256, 10>(tmA, tmB, p, pl, grid, st)
-                   : launch_tc<kModeTopK, 256, 32>(tmA, tmB, p, pl, grid, st);
-    else
-      e = KL == 10 ? launch_tc<kModeTopK, 128, 10>(tmA, tmB, p, pl, grid, st)
-                   : launch_tc<kModeTopK, 128, 32>(tmA, tmB, p, pl, grid, st);
+    static const int dbg_count = env_int("VS_TC_DEBUG_COUNT", 0);
+    unsigned long long* dbg = nullptr;
+    if (dbg_count) {
+      cudaMalloc(&dbg, 4 * sizeof(unsigned long long));
+      cudaMemsetAsync(dbg, 0, 4 * sizeof(unsigned long long), st);
+      p.dbg = dbg;
+    }
+    e = VS_TC_DISPATCH(launch_tc_c, kModeTopK, pl.BN, KL, C, tmA, tmB, p, pl, p.n_slices, st);
     if (e != cudaSuccess) return e;
-    const int nb = min(B - c0 * kTcM, nch * kTcM);
-    e = launch_merge_ex(p.part_s, p.part_r, p.n_slices, p.Bp, nb, KL, k, out_s + (size_t)c0 * kTcM * k,
+    if (dbg) {
+      unsigned long long h[4];
+      cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[tc dbg] C=%d slices=%d tiles/slice=%d: warp-groups=%llu slow-entries=%llu (%.1f%%) hit-lanes=%llu inserts=%llu\n",
+              C, p.n_slices, p.tiles_per_slice, h[0], h[1], 100.0 * h[1] / (h[0] ? h[0] : 1), h[2], h[3]);
+      cudaFree(dbg);
+    }
+    const int nb = (B - c0 * kTcM) < C * kTcM ? (B - c0 * kTcM) : C * kTcM;
+    e = launch_merge_ex(p.part_s, p.part_r, 2 * p.n_slices, p.Bp, nb, KL, k, out_s + (size_t)c0 * kTcM * k,
                         out_r + (size_t)c0 * kTcM * k, st);
     if (e != cudaSuccess) return e;
+    c0 += C;
   }
   return cudaSuccess;
 }
@@ -585,31 +858,29 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a) || F <= 0) return cudaErrorNotSupported;
   const int Bp = (F + kTcM - 1) / kTcM * kTcM;
-  __nv_bfloat16* qb = static_cast<__nv_bfloat16*>(workspace);
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb);
+  const TcWorkspace ws = carve_workspace(workspace, F, a.dim, 1, sm_count, a.n_rows);
+  __nv_bfloat16* qb = ws.q;
+  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb, nullptr);
   count_launch();
   const int chunks_total = Bp / kTcM;
-  for (int c0 = 0; c0 < chunks_total; c0 += sm_count) {
-    const int nch = min(sm_count, chunks_total - c0);
+  for (int c0 = 0; c0 < chunks_total;) {
+    const int C = cluster_for(chunks_total - c0);
     TcParams p;
     fill_common(p, a, pl);
-    p.n_chunks = nch;
-    p.n_slices = max(1, min(sm_count / nch, (int)p.n_tiles));
-    p.tiles_per_slice = (int)((p.n_tiles + p.n_slices - 1) / p.n_slices);
-    p.n_slices = (int)((p.n_tiles + p.tiles_per_slice - 1) / p.tiles_per_slice);
-    p.n_items = p.n_chunks * p.n_slices;
+    const int ncl = VS_TC_DISPATCH10(max_clusters, kModeFilter, pl.BN, C, pl, sm_count);
+    plan_slices(p, ncl);
     p.out_bits = out_bits + (size_t)c0 * kTcM * words_per_filter;
     p.words_per_filter = words_per_filter;
     p.tau = tau;
     p.F = F - c0 * kTcM;
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)nch * kTcM, pl.Dp, pl.Dp, kTcM);
+    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN);
+    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
     if (e != cudaSuccess) return e;
-    e = pl.BN == 256 ? launch_tc<kModeFilter, 256, 10>(tmA, tmB, p, pl, p.n_items, st)
-                     : launch_tc<kModeFilter, 128, 10>(tmA, tmB, p, pl, p.n_items, st);
+    e = VS_TC_DISPATCH10(launch_tc_c, kModeFilter, pl.BN, C, tmA, tmB, p, pl, p.n_slices, st);
     if (e != cudaSuccess) return e;
+    c0 += C;
   }
   return cudaSuccess;
 }
@@ -617,17 +888,20 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
 cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row_hi, float tau, int64_t cap,
                                 int64_t* out_i, int64_t* out_j, float* out_score, unsigned long long* out_count,
                                 void* workspace, int sm_count, cudaStream_t st) {
-  (void)workspace;
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a)) return cudaErrorNotSupported;
+  const TcWorkspace ws = carve_workspace(workspace, kTcM, a.dim, 1, sm_count, a.n_rows);
+  launch_gmin(a, ws, st);
   TcParams p;
   fill_common(p, a, pl);
+  p.gmin = ws.gmin;
   p.a_row_min = row_lo;
   row_lo = row_lo / kTcM * kTcM;   // A blocks are 128-row aligned; rows below the caller's row_lo are filtered out
   p.a_row_lo = row_lo;
   p.a_row_hi = row_hi;
-  p.n_chunks = (int)((row_hi - row_lo + kTcM - 1) / kTcM);
-  p.n_items = p.n_chunks;
+  const int n_blocks = (int)((row_hi - row_lo + kTcM - 1) / kTcM);
+  const int C = cluster_for(n_blocks);
+  p.n_items = (n_blocks + C - 1) / C;
   p.tau = tau;
   p.cap = cap;
   p.out_i = out_i;
@@ -637,11 +911,11 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
   CUtensorMap tmA, tmB;
   cudaError_t e = make_map(&tmA, a.rows, a.n_rows, a.dim, a.ld_elems, kTcM);
   if (e != cudaSuccess) return e;
-  e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN);
+  e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
   if (e != cudaSuccess) return e;
-  const int grid = min(sm_count, p.n_items);
-  return pl.BN == 256 ? launch_tc<kModeDedup, 256, 10>(tmA, tmB, p, pl, grid, st)
-                      : launch_tc<kModeDedup, 128, 10>(tmA, tmB, p, pl, grid, st);
+  int ncl = VS_TC_DISPATCH10(max_clusters, kModeDedup, pl.BN, C, pl, sm_count);
+  if (ncl > p.n_items) ncl = p.n_items;
+  return VS_TC_DISPATCH10(launch_tc_c, kModeDedup, pl.BN, C, tmA, tmB, p, pl, ncl, st);
 }
 
 }  // namespace vs

@@ -74,7 +74,7 @@ struct TensorArgs {
   int64_t row_base;
 };
 // queries: f32 [B][dim] raw (normalised + rounded to bf16 on device into q_bf16 workspace)
-size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count);
+size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count, int64_t n_rows);
 cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k, void* workspace, float* out_s,
                                int64_t* out_r, int sm_count, cudaStream_t st);
 cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int F, float tau, void* workspace,

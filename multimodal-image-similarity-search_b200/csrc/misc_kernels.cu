@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ c
       const int g = c / kin, e = c - g * kin;
       const size_t src = ((size_t)g * Bstride + b) * kin + e;
       const float s = cs[src];
-      if (cr[src] >= 0 && s == s) key = ((uint64_t)score_key(s) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)c);
+      // ties in score rank by ascending ROW (lists may interleave row ranges), so the row itself is
+      // the low half of the key; global rows are < 2^32 (documented collection limit)
+      if (cr[src] >= 0 && s == s) key = ((uint64_t)score_key(s) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)cr[src]);
     }
     keys[c] = key;
   }
@@ -194,11 +196,8 @@ __global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ c
     float s = VS_NEG_INF;
     int64_t r = -1;
     if (key != 0) {
-      const int c = (int)(0xFFFFFFFFu - (uint32_t)key);
-      const int g = c / kin, ee = c - g * kin;
-      const size_t src = ((size_t)g * Bstride + b) * kin + ee;
-      s = cs[src];
-      r = cr[src];
+      s = key_score((uint32_t)(key >> 32));
+      r = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
     }
     out_s[(size_t)b * kout + e] = s;
     out_r[(size_t)b * kout + e] = r;
