@@ -49,6 +49,7 @@ class ShardedSearcher:
         if self._gs is None or self._gs.shape != (self.world_size, B, k) or self._gs.device != s.device:
             self._gs = torch.empty((self.world_size, B, k), dtype=torch.float32, device=s.device)
             self._gr = torch.empty((self.world_size, B, k), dtype=torch.int64, device=s.device)
-        self._dist.all_gather_into_tensor(self._gs, s.contiguous(), group=self.group)
-        self._dist.all_gather_into_tensor(self._gr, r.contiguous(), group=self.group)
+        # [G*B, k] view: the concatenating form is accepted by both NCCL and gloo
+        self._dist.all_gather_into_tensor(self._gs.view(-1, k), s.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(self._gr.view(-1, k), r.contiguous(), group=self.group)
         return self.merge(self._gs, self._gr)

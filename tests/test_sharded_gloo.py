@@ -1,0 +1,74 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (row partition, candidate all-gather, merge) gives
+the same answer as a single shard.  The local search and the merge are injected (oracle here, the
+CUDA kernels in production -- see ShardedSearcher.for_index)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmiss_b200.sharded import ShardedSearcher, shard_bounds
+from oracle import cosine_oracle as O
+
+
+def test_shard_bounds_cover_rows_exactly():
+    for n, g in ((10_000_000, 8), (10, 3), (7, 8), (0, 2), (1_000_001, 4)):
+        spans = [shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) == (n + g - 1) // g if n else True
+
+
+def _worker(rank, world, port, n, d, k, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[n - 1] = X[3]                                   # an exact tie across shards
+    Q = np.concatenate([rng.standard_normal((4, d)).astype(np.float32), X[3:4]])
+    lo, hi = shard_bounds(n, world, rank)
+
+    def local_topk(q, kk):
+        s, r = O.cosine_topk(q.numpy(), X[lo:hi], kk)
+        S = torch.full((q.shape[0], kk), float("-inf"))
+        R = torch.full((q.shape[0], kk), -1, dtype=torch.int64)
+        S[:, :s.shape[1]], R[:, :r.shape[1]] = torch.from_numpy(s), torch.from_numpy(r + lo)
+        return S, R
+
+    def merge(cs, cr):
+        s, r = O.merge_topk(cs.numpy(), cr.numpy(), cs.shape[2])
+        return torch.from_numpy(s), torch.from_numpy(r)
+
+    searcher = ShardedSearcher(local_topk, merge)
+    assert searcher.world_size == world and searcher.rank == rank
+    s, r = searcher.search(torch.from_numpy(Q), k)
+    full = O.cosine_scores(Q, X)
+    for b in range(Q.shape[0]):
+        ok, why = O.topk_matches(s[b].numpy(), r[b].numpy(), full[b], k, 1e-6)
+        assert ok, why
+    assert r[4][:2].tolist() == [3, n - 1]            # tie resolved by global row on every rank
+    got = [torch.zeros_like(r) for _ in range(world)]
+    dist.all_gather(got, r)
+    assert all(torch.equal(got[0], g) for g in got)   # every rank ends with the same answer
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_2_matches_single_shard():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1001, 32, 10, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
