@@ -18,6 +18,8 @@
 //     CTA to finish (ticket) merges all CTA lists and writes the final [k] result: no second
 //     kernel, no score materialisation.
 // Algorithmic HBM bytes per query = n_rows * (pitch + 4).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -122,6 +124,11 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKe
     fence_mbar_init();
   }
   __syncthreads();
+  // PDL: the next query's kernel may start filling SMs as this grid's CTAs retire.  This kernel
+  // only READS the corpus/query until the partial lists are written, so the wait on the previous
+  // grid (which may still be merging into the same workspace) is deferred to that point.
+  pdl_launch_dependents();
+  if constexpr (M == 0) pdl_wait();   // the materialising variant writes shared scratch while scanning
 
   WarpTopK<ML> top;
   top.init();
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKe
   }
 
   if constexpr (M == 0) return;
+  pdl_wait();   // previous grid fully done: its partial lists / tickets / result rows are no longer in use
 
   // ---- per-CTA merge of the 8 warp lists ---------------------------------------------------
   if (warp < kConsumerWarps) top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
@@ -360,9 +368,23 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   if ((uint32_t)gx > p.n_tiles) gx = (int)p.n_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, a.B, 1);
-  kern<<<grid, kScanThreads, smem, st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kScanThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = [] {
+    const char* v = getenv("VS_SCAN_PDL");
+    return !(v && v[0] == '0');
+  }();
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, p);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 template <typename T, int CPL, int W, bool FULL>
