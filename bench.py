@@ -6,8 +6,10 @@
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # N ranks, one GPU each
 
 A *step* is one batch of Q independent single queries over the whole corpus: every query is its
-own fused scan kernel launch that streams the rank's shard from HBM once (K1), then the ranks'
-[Q, k] candidates are exchanged with one NCCL all-gather and merged on every rank (K5).  The
+own fused scan kernel launch that streams the rank's shard from HBM once (K1).  With N > 1 the LAST
+CTA of that same kernel stores the shard's k candidates into every peer's exchange buffer over
+NVLink (P2P stores + flags) and merges the N lists, so every rank ends with the global top-k and
+the query is still ONE kernel, no NCCL call (--exchange nccl: all-gather + merge kernel K5).  The
 corpus (10M rows total, row-sharded ceil(N/G) per rank => "strong" scaling) is resident in HBM
 before the timed region; it is >> L2 (126 MB), so no flush is needed between iterations.
 
@@ -37,6 +39,23 @@ DIM = 512
 TOPK = 10
 METRIC = "exact top-10 cosine search QPS, 10Mx512 bf16 corpus, single-query scans"
 HBM_FALLBACK_GBS = 6650.0
+
+
+def ncu_traffic_bytes(rows_local: int, dim: int, dtype: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per scan launch from the committed `ncu --set full`
+    capture (profiles/r01_ncu_scan_topk.txt, taken on 10M x 512 bf16); None for any other shape."""
+    if (rows_local, dim, dtype) != (10_000_000, 512, "bf16"):
+        return None
+    try:
+        total = 0.0
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_scan_topk.txt")):
+            if "dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln:
+                val, unit = ln.split("=")[1].split()
+                total += float(val) * scale[unit]
+        return total or None
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -209,7 +228,24 @@ def run_ours(args):
     k = args.k
     cand_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
     cand_r = torch.empty((Q, k), dtype=torch.int64, device=dev)
-    searcher = M.ShardedSearcher.for_index(ix, mode="scan") if G > 1 else None
+    searcher, exchange = None, "none"
+    if G > 1:
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                searcher = M.ShardedSearcher.for_index(ix, mode="scan", exchange="p2p",
+                                                       b_max=max(Q, args.batch, 1), k_max=max(32, args.k))
+            except Exception as e:                                   # e.g. no peer access between the GPUs
+                exchange = f"nccl (p2p unavailable: {type(e).__name__}: {e})"[:200]
+            flag = torch.tensor([1 if searcher is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # all ranks use the same exchange
+            if int(flag.item()) == 0:
+                if searcher is not None:
+                    exchange = "nccl (p2p unavailable on a peer)"
+                searcher = None
+        if searcher is None:
+            searcher = M.ShardedSearcher.for_index(ix, mode="scan", exchange="nccl")
+    p2p = searcher is not None and searcher.exchange == "p2p"
     gath_s = torch.empty((G, Q, k), dtype=torch.float32, device=dev) if G > 1 else None
     gath_r = torch.empty((G, Q, k), dtype=torch.int64, device=dev) if G > 1 else None
     out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
@@ -220,11 +256,17 @@ def run_ours(args):
         if timed:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        for i in range(Q):                       # Q independent single-query scans (one kernel each)
-            ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan")
+        if p2p:                                  # scan + NVLink exchange + merge fused: one kernel per query
+            for i in range(Q):
+                ix.query_sharded_dev(q_dev[i:i + 1], k, out_scores=out_s[i:i + 1], out_rows=out_r[i:i + 1], mode="scan")
+        else:
+            for i in range(Q):                   # Q independent single-query scans (one kernel each)
+                ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan")
         if timed:
             e1.record()
             scan_ev.append((e0, e1))
+        if p2p:
+            return out_s, out_r
         if G > 1:
             dist.all_gather_into_tensor(gath_s, cand_s)
             dist.all_gather_into_tensor(gath_r, cand_r)
@@ -300,6 +342,9 @@ def run_ours(args):
 
         def bstep():
             ix.blend_dev(img, txt, wts, out=qb)                      # multimodal blend (main.py:850-860)
+            if p2p:
+                ix.query_sharded_dev(qb, k, out_scores=bos, out_rows=bor, mode="tensor")   # K2 + exchange kernel
+                return
             ix.query_dev(qb, k, out_scores=bs, out_rows=br, mode="tensor")
             if G > 1:
                 dist.all_gather_into_tensor(bgs.view(-1, k), bs)
@@ -318,6 +363,9 @@ def run_ours(args):
         batched_ms = b0.elapsed_time(b1) / 5
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------
+    xerr = ix.exchange_error() if p2p else 0
+    if xerr:
+        raise SystemExit(f"bench.py: peer exchange timed out on rank {rank} (results invalid)")
     tvals = torch.tensor([elapsed_ms, scan_ms, e2e_s, batched_ms], dtype=torch.float64, device=dev)
     if G > 1:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
@@ -335,17 +383,19 @@ def run_ours(args):
             "scanned_gb_per_s": qps * args.rows * args.dim * (2 if args.dtype == "bf16" else 4) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "peak_kind": peaks_kind, "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": ncu_traffic_bytes(n_local, args.dim, args.dtype),
                          "bytes_per_launch": rows_bytes, "avg_launch_ms": scan_ms},
             "e2e": {"value": Q * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q * args.dim * 4,
                     "d2h_bytes_per_step": Q * k * 12, "steps": e2e_steps,
-                    "path": "vs_query_topk_host (ctypes)" if G == 1 else "ShardedSearcher.search + pinned H2D/D2H"},
-            "gpu_launches": int(launches), "clocks": clocks, "build_s": t_build,
+                    "path": "vs_query_topk_host (ctypes)" if G == 1 else
+                    f"ShardedSearcher.search ({'fused p2p exchange' if p2p else 'nccl all-gather + merge'}) + pinned H2D/D2H"},
+            "gpu_launches": int(launches), "clocks": clocks, "build_s": t_build, "exchange": exchange,
         }
         if batched_ms > 0:
             tf = 2.0 * args.batch * args.rows * args.dim / (batched_ms / 1e3) / 1e12
             line["batched"] = {"workload": f"{args.batch} blended text+image queries, top-{k}, tcgen05 path "
-                                           f"(blend kernel + K2{' + all-gather + merge' if G > 1 else ''})",
+                                           f"(blend kernel + K2{(' + p2p exchange kernel' if p2p else ' + all-gather + merge') if G > 1 else ''})",
                                "ms_per_batch": batched_ms, "qps": args.batch / (batched_ms / 1e3), "tflops": tf,
                                "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
                                "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"]}
@@ -369,6 +419,8 @@ def main():
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--queries", type=int, default=32, help="single-query scans per step")
     ap.add_argument("--batch", type=int, default=1024, help="batched tensor-path extra (0 = skip)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: candidate exchange fused into the query kernel over NVLink peer memory, or NCCL all-gather")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -126,6 +126,35 @@ int vs_query_multimodal_host(vs_index_t* ix, const float* img, const float* txt,
 int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev,
                       int G, int B, int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
 
+/* ---- sharded query with the exchange fused in (replaces local query +
+ *      ncclAllGather + vs_merge_topk_dev).  Every rank (one process per GPU, or several handles in
+ *      one process) owns an exchange buffer that all G ranks have mapped over NVLink peer memory:
+ *        1. vs_exchange_create(ix, G, rank, B_max, k_max)    allocate + zero the local buffer
+ *        2. vs_exchange_ipc_handle(ix, h)                    64-byte cudaIpcMemHandle_t to publish
+ *           (or vs_exchange_local_ptr for handles living in the same process)
+ *        3. vs_exchange_attach(ix, handles, peer_ptrs)       map the peers' buffers: for peer g the
+ *           pointer peer_ptrs[g] is used when given, else handles[64*g..] is opened with
+ *           cudaIpcOpenMemHandle (entry `rank` is ignored).  Call after ALL ranks finished step 1.
+ *      vs_query_topk_sharded_dev then behaves like vs_query_topk_dev but returns the GLOBAL top-k
+ *      on every rank: for B <= 64 on the scan path the LAST CTA of the fused scan kernel stores
+ *      the shard's k candidates straight into every peer's buffer (P2P stores), raises per-query
+ *      flags (st.release.sys), spins (bounded) on the G local flags and merges -- one kernel per
+ *      query, no NCCL call, no host synchronisation.  Larger batches / the tcgen05 path run the
+ *      local query and one exchange kernel with the same wire protocol.  All ranks must issue the
+ *      same sequence of sharded queries (same B, k); k <= k_max <= 128; global rows < 2^32.
+ *      vs_exchange_merge_dev exposes the exchange kernel alone for caller-made [B,k] candidates.
+ *      vs_exchange_error() != 0 (after a synchronise) means a peer never arrived: results invalid. */
+size_t vs_exchange_bytes(int B_max, int k_max, int G);
+int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max);
+int vs_exchange_ipc_handle(vs_index_t* ix, unsigned char handle_out[64]);
+void* vs_exchange_local_ptr(vs_index_t* ix);
+int vs_exchange_attach(vs_index_t* ix, const unsigned char* ipc_handles, void* const* peer_ptrs);
+int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits,
+                              int mode, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B,
+                          int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+int vs_exchange_error(vs_index_t* ix);
+
 /* ---- filter sweep (BASELINE config 4; CLIP-side analogue of process_filter_on_all_images,
  *      backend/app/main.py:939-1056): prompts [F, dim] float32 (host or device) -> bit mask
  *      out_bits[F][words_per_filter] (uint32, bit n%32 of word n/32 set <=> cos >= tau),

@@ -46,6 +46,14 @@ SYMBOLS = {
     "vs_blend_dev": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "vs_query_multimodal_host": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p]),
     "vs_merge_topk_dev": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "vs_exchange_bytes": (C.c_size_t, [_i, _i, _i]),
+    "vs_exchange_create": (_i, [_p, _i, _i, _i, _i]),
+    "vs_exchange_ipc_handle": (_i, [_p, _p]),
+    "vs_exchange_local_ptr": (_p, [_p]),
+    "vs_exchange_attach": (_i, [_p, _p, _p]),
+    "vs_query_topk_sharded_dev": (_i, [_p, _p, _i, _i, _p, _i, _p, _p, _p]),
+    "vs_exchange_merge_dev": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
+    "vs_exchange_error": (_i, [_p]),
     "vs_filter_words": (_i64, [_p]),
     "vs_filter_sweep_dev": (_i, [_p, _p, _i, _f, _p, _p]),
     "vs_filter_sweep_host": (_i, [_p, _p, _i, _f, _p]),

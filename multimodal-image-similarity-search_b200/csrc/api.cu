@@ -95,9 +95,20 @@ struct vs_index {
   bool last_stream_valid = false;
   std::mutex mu;
   // scratch
-  DevBuf d_q, d_out_s, d_out_r, d_part_s, d_part_r, d_tickets, d_scores, d_select, d_tensor, d_stage, d_misc;
+  DevBuf d_q, d_out_s, d_out_r, d_part_s, d_part_r, d_tickets, d_scores, d_select, d_tensor, d_stage, d_misc, d_err;
   HostBuf h_in, h_out;
   size_t tickets_n = 0;
+  // peer exchange (row-sharded collection): local buffer + the peers' mappings
+  struct Exchange {
+    int G = 0, rank = 0, Bmax = 0, kmax = 0;
+    size_t bytes = 0;
+    void* local = nullptr;
+    void* peers[vs::kMaxPeers] = {};
+    bool ipc_opened[vs::kMaxPeers] = {};
+    bool attached = false;
+    uint32_t epoch = 0;
+  } xc;
+  DevBuf d_xs, d_xr;
 };
 
 namespace {
@@ -190,8 +201,26 @@ cudaStream_t pick_stream(vs_index* ix, void* stream) { return stream ? (cudaStre
 // queries per scan launch (bounds the partial-list workspace)
 constexpr int kScanBatch = 64;
 
+// fills the kernel-side exchange descriptor for the NEXT exchange (advances the epoch)
+vs::XchgParams next_exchange(vs_index* ix, int slot0) {
+  vs::XchgParams x = {};
+  for (int g = 0; g < ix->xc.G; ++g) x.peers[g] = static_cast<unsigned char*>(ix->xc.peers[g]);
+  x.err = (unsigned int*)ix->d_err.p;
+  x.G = ix->xc.G;
+  x.rank = ix->xc.rank;
+  x.Bmax = ix->xc.Bmax;
+  x.kmax = ix->xc.kmax;
+  x.slot0 = slot0;
+  if (++ix->xc.epoch == 0) ix->xc.epoch = 2;   // 0 is the "never written" flag value; keep the parity sequence
+  x.epoch = ix->xc.epoch;
+  return x;
+}
+
+// `fused_exchange`: when non-null and the query takes the fused scan path in ONE launch, the
+// exchange is done by the scan kernel itself and *fused_exchange is set to true.
 int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint64_t* req, int mode, float* out_s,
-                     int64_t* out_r, cudaStream_t st) {
+                     int64_t* out_r, cudaStream_t st, bool* fused_exchange = nullptr) {
+  if (fused_exchange) *fused_exchange = false;
   if (B <= 0) return VS_OK;
   if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
   // the scratch buffers (partial lists, tickets, select state) are shared by all queries of this
@@ -281,6 +310,10 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     a.out_s = out_s + (size_t)b0 * k;
     a.out_r = out_r + (size_t)b0 * k;
     a.scores_full = large_k ? (float*)ix->d_scores.p : nullptr;
+    if (fused_exchange && !large_k && B <= step) {
+      a.xg = next_exchange(ix, 0);
+      *fused_exchange = true;
+    }
     CU(vs::launch_scan(a, ix->sm_count, st));
     if (large_k)
       CU(vs::launch_select((const float*)ix->d_scores.p, ix->n, nb, k, ix->row_base, ix->d_select.p, a.out_s, a.out_r, st));
@@ -350,12 +383,18 @@ int vs_destroy(vs_index_t* ix) {
   if (ix->inv) cudaFree(ix->inv);
   if (ix->mask) cudaFree(ix->mask);
   DevBuf* bufs[] = {&ix->d_q,       &ix->d_out_s,  &ix->d_out_r,  &ix->d_part_s, &ix->d_part_r, &ix->d_tickets,
-                    &ix->d_scores,  &ix->d_select, &ix->d_tensor, &ix->d_stage,  &ix->d_misc};
+                    &ix->d_scores,  &ix->d_select, &ix->d_tensor, &ix->d_stage,  &ix->d_misc,   &ix->d_err};
   for (DevBuf* b : bufs) b->release();
   ix->h_in.release();
   ix->h_out.release();
+  for (int g = 0; g < vs::kMaxPeers; ++g)
+    if (ix->xc.ipc_opened[g]) cudaIpcCloseMemHandle(ix->xc.peers[g]);
+  if (ix->xc.local) cudaFree(ix->xc.local);
+  ix->d_xs.release();
+  ix->d_xr.release();
   if (ix->ev) cudaEventDestroy(ix->ev);
   cudaStreamDestroy(ix->stream);
+  cudaGetLastError();
   delete ix;
   return VS_OK;
 }
@@ -594,6 +633,176 @@ int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_
     CU(vs::launch_merge(cand_scores_dev, cand_rows_dev, G, B, k, out_scores_dev, out_rows_dev, st));
   }
   return VS_OK;
+}
+
+size_t vs_exchange_bytes(int B_max, int k_max, int G) {
+  if (B_max <= 0 || k_max <= 0 || G <= 0 || G > vs::kMaxPeers) return 0;
+  return vs::exchange_bytes(B_max, k_max, G);
+}
+
+int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (G <= 0 || G > vs::kMaxPeers || rank < 0 || rank >= G)
+    return fail(VS_ERR_ARG, "need 1 <= G <= %d and 0 <= rank < G", vs::kMaxPeers);
+  if (B_max <= 0 || B_max > 65536 || k_max <= 0 || k_max > vs::kMaxFusedK)
+    return fail(VS_ERR_ARG, "need 1 <= B_max <= 65536 and 1 <= k_max <= %d", vs::kMaxFusedK);
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (ix->xc.local) return fail(VS_ERR_ARG, "exchange already created for this index");
+  DeviceGuard g(ix->device);
+  const size_t bytes = vs::exchange_bytes(B_max, k_max, G);
+  // plain cudaMalloc (not a pool allocation): required for cudaIpcGetMemHandle
+  CU(cudaMalloc(&ix->xc.local, bytes));
+  CU(cudaMemset(ix->xc.local, 0, bytes));
+  CU(ix->d_err.reserve(16));
+  CU(cudaMemset(ix->d_err.p, 0, 16));
+  CU(cudaDeviceSynchronize());
+  ix->xc.G = G;
+  ix->xc.rank = rank;
+  ix->xc.Bmax = B_max;
+  ix->xc.kmax = k_max;
+  ix->xc.bytes = bytes;
+  ix->xc.peers[rank] = ix->xc.local;
+  ix->xc.attached = (G == 1);
+  return VS_OK;
+}
+
+int vs_exchange_ipc_handle(vs_index_t* ix, unsigned char handle_out[64]) {
+  if (!ix || !handle_out) return fail(VS_ERR_ARG, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->xc.local) return fail(VS_ERR_ARG, "vs_exchange_create has not been called");
+  DeviceGuard g(ix->device);
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ix->xc.local));
+  memcpy(handle_out, &h, 64);
+  return VS_OK;
+}
+
+void* vs_exchange_local_ptr(vs_index_t* ix) { return ix ? ix->xc.local : nullptr; }
+
+int vs_exchange_attach(vs_index_t* ix, const unsigned char* ipc_handles, void* const* peer_ptrs) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->xc.local) return fail(VS_ERR_ARG, "vs_exchange_create has not been called");
+  if (ix->xc.attached && ix->xc.G > 1) return fail(VS_ERR_ARG, "exchange already attached");
+  DeviceGuard g(ix->device);
+  for (int p = 0; p < ix->xc.G; ++p) {
+    if (p == ix->xc.rank) continue;
+    if (peer_ptrs && peer_ptrs[p]) {
+      // a pointer of this process: make sure this device may dereference it
+      cudaPointerAttributes at;
+      CU(cudaPointerGetAttributes(&at, peer_ptrs[p]));
+      if (at.type != cudaMemoryTypeDevice) return fail(VS_ERR_ARG, "peer pointer %d is not device memory", p);
+      if (at.device != ix->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ix->device, at.device));
+        if (!can) return fail(VS_ERR_UNSUPPORTED, "device %d cannot access peer device %d", ix->device, at.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+      }
+      ix->xc.peers[p] = peer_ptrs[p];
+    } else if (ipc_handles) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, ipc_handles + (size_t)64 * p, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VS_ERR_CUDA, "cudaIpcOpenMemHandle(peer %d): %s", p, cudaGetErrorString(e));
+      }
+      ix->xc.peers[p] = ptr;
+      ix->xc.ipc_opened[p] = true;
+    } else {
+      return fail(VS_ERR_ARG, "no pointer or IPC handle for peer %d", p);
+    }
+  }
+  ix->xc.attached = true;
+  return VS_OK;
+}
+
+namespace {
+int exchange_ready(vs_index* ix, int k) {
+  if (!ix->xc.local || !ix->xc.attached) return fail(VS_ERR_ARG, "exchange not created/attached");
+  if (k <= 0 || k > ix->xc.kmax) return fail(VS_ERR_UNSUPPORTED, "k=%d exceeds the exchange's k_max=%d", k, ix->xc.kmax);
+  if (ix->row_base < 0 || ix->row_base + ix->n > 0xFFFFFFF0LL)
+    return fail(VS_ERR_UNSUPPORTED, "sharded queries need global rows < 2^32");
+  return VS_OK;
+}
+// the exchange kernel on [B,k] candidates, in chunks of B_max slots
+int exchange_chunks(vs_index* ix, const float* cs, const int64_t* cr, int B, int k, float* out_s, int64_t* out_r,
+                    cudaStream_t st) {
+  for (int b0 = 0; b0 < B; b0 += ix->xc.Bmax) {
+    const int nb = B - b0 < ix->xc.Bmax ? B - b0 : ix->xc.Bmax;
+    const vs::XchgParams x = next_exchange(ix, 0);
+    CU(vs::launch_exchange_merge(cs + (size_t)b0 * k, cr + (size_t)b0 * k, x, nb, k, out_s + (size_t)b0 * k,
+                                 out_r + (size_t)b0 * k, ix->sm_count, st));
+  }
+  return VS_OK;
+}
+}  // namespace
+
+int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits, int mode,
+                              float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B <= 0 || !q_dev || !out_scores_dev || !out_rows_dev) return fail(VS_ERR_ARG, "bad B or NULL buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  int rc = exchange_ready(ix, k);
+  if (rc) return rc;
+  cudaStream_t st = pick_stream(ix, stream);
+  if (ix->xc.G == 1) return query_dev_locked(ix, q_dev, B, k, require_bits, mode, out_scores_dev, out_rows_dev, st);
+  // try the fused form first: the local result never leaves the scan kernel
+  CU(ix->d_xs.reserve((size_t)B * k * sizeof(float)));
+  CU(ix->d_xr.reserve((size_t)B * k * sizeof(int64_t)));
+  bool fused = false;
+  int path = mode;
+  if (path == VS_Q_AUTO)
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+            vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
+  if (path == VS_Q_SCAN && ix->n > 0 && B <= kScanBatch) {
+    rc = query_dev_locked(ix, q_dev, B, k, require_bits, VS_Q_SCAN, out_scores_dev, out_rows_dev, st, &fused);
+    if (rc) return rc;
+    if (fused) return VS_OK;
+    // (a filter without bits produced an all-empty local result in out_*: exchange it below)
+    CU(cudaMemcpyAsync(ix->d_xs.p, out_scores_dev, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(ix->d_xr.p, out_rows_dev, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    rc = query_dev_locked(ix, q_dev, B, k, require_bits, path, (float*)ix->d_xs.p, (int64_t*)ix->d_xr.p, st);
+    if (rc) return rc;
+  }
+  return exchange_chunks(ix, (const float*)ix->d_xs.p, (const int64_t*)ix->d_xr.p, B, k, out_scores_dev, out_rows_dev, st);
+}
+
+int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B, int k,
+                          float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B <= 0 || !cand_scores_dev || !cand_rows_dev || !out_scores_dev || !out_rows_dev)
+    return fail(VS_ERR_ARG, "bad B or NULL buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  int rc = exchange_ready(ix, k);
+  if (rc) return rc;
+  cudaStream_t st = pick_stream(ix, stream);
+  // exchanges of one index are ordered: serialise against the stream that ran the previous one
+  if (ix->last_stream_valid && ix->last_stream != st) {
+    CU(cudaEventRecord(ix->ev, ix->last_stream));
+    CU(cudaStreamWaitEvent(st, ix->ev, 0));
+  }
+  ix->last_stream = st;
+  ix->last_stream_valid = true;
+  return exchange_chunks(ix, cand_scores_dev, cand_rows_dev, B, k, out_scores_dev, out_rows_dev, st);
+}
+
+int vs_exchange_error(vs_index_t* ix) {
+  if (!ix || !ix->d_err.p) return 0;
+  DeviceGuard g(ix->device);
+  unsigned int v = 0;
+  if (cudaMemcpy(&v, ix->d_err.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (int)v;
 }
 
 int64_t vs_filter_words(const vs_index_t* ix) {

@@ -1,0 +1,96 @@
+// exchange.cuh -- candidate exchange between the row shards over NVLink peer memory
+// ("each GPU does its local top-k ... k-way merge produces the global
+// result"; here the all-gather is replaced by P2P stores issued from inside the query kernel).
+//
+// Every rank owns one exchange buffer that all G ranks have mapped.  For one query slot a warp
+//   1. push   : stores its k (score, global row) candidates into list [rank] of the slot in
+//               EVERY rank's buffer (plain st.global on peer-mapped addresses -> NVLink writes),
+//   2. signal : __threadfence_system, then st.release.sys of `epoch` into flag [slot][rank] of
+//               every rank,
+//   3. wait   : ld.acquire.sys spin on the G LOCAL flags of the slot (bounded, sets *err),
+//   4. merge  : merges the G lists that now sit in LOCAL memory into its register top-k list.
+// The buffer has two halves selected by epoch parity.  A rank can be at most one exchange ahead
+// of any peer: completing exchange e needs every peer's flag of e, and a peer raises it only after
+// its own exchange e-1 finished (stream order / griddepcontrol.wait), so when half (e & 1) is
+// overwritten by exchange e+2 every rank has already merged exchange e out of it.
+// Half layout: flags u32 [Bmax][8] | scores f32 [G][Bmax][kmax] | rows u32 [G][Bmax][kmax].
+#pragma once
+#include "common.cuh"
+
+namespace vs {
+
+constexpr int kMaxPeers = 8;
+
+struct XchgParams {
+  unsigned char* peers[kMaxPeers];   // peer-mapped base pointers; peers[rank] is the local buffer
+  unsigned int* err;                 // device flag: set to 1 when a wait timed out
+  int G;                             // 0 = no exchange
+  int rank;
+  int Bmax, kmax;
+  int slot0;                         // slot of query 0 of this launch
+  uint32_t epoch;
+};
+
+struct XchgLayout {
+  size_t half_bytes, scores_off, rows_off;
+};
+__host__ __device__ inline XchgLayout xchg_layout(int Bmax, int kmax, int G) {
+  XchgLayout L;
+  size_t off = (size_t)Bmax * kMaxPeers * sizeof(uint32_t);
+  off = (off + 255) & ~(size_t)255;
+  L.scores_off = off;
+  off += (size_t)G * Bmax * kmax * sizeof(float);
+  off = (off + 255) & ~(size_t)255;
+  L.rows_off = off;
+  off += (size_t)G * Bmax * kmax * sizeof(uint32_t);
+  L.half_bytes = (off + 255) & ~(size_t)255;
+  return L;
+}
+
+// steps 1 + 2 (warp-collective).  `top` holds GLOBAL rows.
+template <int M>
+__device__ __forceinline__ void xchg_push(const XchgParams& x, const WarpTopK<M>& top, int slot, int k, int lane) {
+  const XchgLayout L = xchg_layout(x.Bmax, x.kmax, x.G);
+  const size_t half = (size_t)(x.epoch & 1u) * L.half_bytes;
+  const size_t list = ((size_t)x.rank * x.Bmax + slot) * x.kmax;
+  for (int g = 0; g < x.G; ++g) {
+    unsigned char* base = x.peers[g] + half;
+    top.store(reinterpret_cast<float*>(base + L.scores_off) + list,
+              reinterpret_cast<uint32_t*>(base + L.rows_off) + list, k, lane);
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < x.G) {
+    uint32_t* flag = reinterpret_cast<uint32_t*>(x.peers[lane] + half) + (size_t)slot * kMaxPeers + x.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
+  }
+}
+
+// steps 3 + 4 (warp-collective): `top` is re-initialised and receives the global top-k.
+template <int M>
+__device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>& top, int slot, int k, int lane) {
+  const XchgLayout L = xchg_layout(x.Bmax, x.kmax, x.G);
+  const size_t half = (size_t)(x.epoch & 1u) * L.half_bytes;
+  const unsigned char* mine = x.peers[x.rank] + half;
+  if (lane < x.G) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine) + (size_t)slot * kMaxPeers + lane;
+    const long long t0 = clock64();
+    uint32_t v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v == x.epoch) break;
+      if (clock64() - t0 > 6000000000LL) {   // ~3 s: a peer never arrived
+        atomicExch(x.err, 1u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncwarp();
+  top.init();
+  const volatile float* ls = reinterpret_cast<const volatile float*>(mine + L.scores_off) + (size_t)slot * x.kmax;
+  const volatile uint32_t* lr = reinterpret_cast<const volatile uint32_t*>(mine + L.rows_off) + (size_t)slot * x.kmax;
+  top.merge_from(ls, lr, x.G, x.Bmax * x.kmax, k, lane);
+}
+
+}  // namespace vs

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "exchange.cuh"
+
 namespace vs {
 
 constexpr int kMaskWords = 4;
@@ -45,6 +47,7 @@ struct ScanArgs {
   float* out_s;              // [B][k]
   int64_t* out_r;            // [B][k]
   float* scores_full;        // [B][n_rows] when materialising for the large-k path, else nullptr
+  XchgParams xg = {};        // xg.G > 0: fused peer exchange of the result (B <= 64, k <= 128)
 };
 // returns cudaErrorInvalidValue when (dtype, ld_bytes) has no instantiation
 cudaError_t launch_scan(const ScanArgs& a, int sm_count, cudaStream_t st);
@@ -54,6 +57,10 @@ int scan_rows_per_tile(int dtype, int64_t ld_bytes);
 // [G][B][k] candidates (global rows, <0 empty) -> [B][k]
 cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
                          cudaStream_t st);
+// the exchange kernel alone: [B][k] candidates (global rows, <0 empty) of this rank -> global [B][k]
+size_t exchange_bytes(int Bmax, int kmax, int G);
+cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
+                                  int64_t* out_r, int sm_count, cudaStream_t st);
 // general form: candidates [G][Bstride][kin] -> [B][kout]
 cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
                             float* out_s, int64_t* out_r, cudaStream_t st);

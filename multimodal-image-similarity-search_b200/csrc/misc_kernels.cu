@@ -1,6 +1,7 @@
 // misc_kernels.cu -- K6 ingest (cast + inverse norm), export, multimodal blend, K5 candidate
 // merge (block bitonic), and the exact radix select used for k > 128.
 #include "common.cuh"
+#include "exchange.cuh"
 #include "kernels.h"
 
 namespace vs {
@@ -226,6 +227,70 @@ cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstri
 cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k, float* out_s, int64_t* out_r,
                          cudaStream_t st) {
   return launch_merge_ex(cs, cr, G, B, B, k, k, out_s, out_r, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// The peer exchange as a kernel of its own (protocol: exchange.cuh), for candidates produced by
+// the tcgen05 path or by batches larger than one fused scan launch.  One warp per query slot.
+// The grid never exceeds the SM count, so every CTA is resident; each warp first pushes ALL of its
+// queries and only then starts waiting, so no rank can wait on a push that has not been issued.
+// ------------------------------------------------------------------------------------------
+size_t exchange_bytes(int Bmax, int kmax, int G) { return 2 * xchg_layout(Bmax, kmax, G).half_bytes; }
+
+constexpr int kXchgWarps = 8;
+
+template <int M>
+__device__ __forceinline__ void load_candidates(WarpTopK<M>& top, const float* cs, const int64_t* cr, int k, int lane) {
+  top.init();
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int p = m * 32 + lane;
+    if (p < k && cr[p] >= 0) {
+      top.s[m] = cs[p];
+      top.r[m] = (uint32_t)cr[p];
+    }
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kXchgWarps * 32) exchange_merge_kernel(const float* __restrict__ cs,
+                                                                         const int64_t* __restrict__ cr, XchgParams x, int B,
+                                                                         int k, float* __restrict__ out_s,
+                                                                         int64_t* __restrict__ out_r) {
+  const int lane = threadIdx.x & 31;
+  const int w0 = blockIdx.x * kXchgWarps + (threadIdx.x >> 5);
+  const int nw = gridDim.x * kXchgWarps;
+  WarpTopK<M> top;
+  for (int b = w0; b < B; b += nw) {
+    load_candidates(top, cs + (size_t)b * k, cr + (size_t)b * k, k, lane);
+    xchg_push(x, top, x.slot0 + b, k, lane);
+  }
+  for (int b = w0; b < B; b += nw) {
+    xchg_wait_merge(x, top, x.slot0 + b, k, lane);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const int p = m * 32 + lane;
+      if (p < k) {
+        out_s[(size_t)b * k + p] = top.s[m];
+        out_r[(size_t)b * k + p] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m];
+      }
+    }
+  }
+}
+
+cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
+                                  int64_t* out_r, int sm_count, cudaStream_t st) {
+  if (x.G <= 0 || x.G > kMaxPeers || x.rank < 0 || x.rank >= x.G || B <= 0 || x.slot0 + B > x.Bmax || k <= 0 ||
+      k > x.kmax || k > kMaxFusedK)
+    return cudaErrorInvalidValue;
+  int grid = (B + kXchgWarps - 1) / kXchgWarps;
+  if (grid > sm_count) grid = sm_count;
+  if (k <= 32)
+    exchange_merge_kernel<1><<<grid, kXchgWarps * 32, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+  else
+    exchange_merge_kernel<4><<<grid, kXchgWarps * 32, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+  count_launch();
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "exchange.cuh"
 #include "kernels.h"
 
 namespace vs {
@@ -54,7 +55,32 @@ struct ScanKernelParams {
   int stages;
   int stage_stride;   // bytes between row stages
   int use_mask;
+  XchgParams xg;      // xg.G > 0: exchange the shard's result with the peers before writing it
 };
+
+// Final step of a query, executed by ONE warp holding the shard's top-k (local rows): either write
+// it out, or (row-sharded collection) push it to every peer over NVLink, wait for the peers'
+// lists and write the merged GLOBAL top-k.  Exactly one warp per query reaches this point, and it
+// never waits before its own push, so ranks cannot deadlock on each other.
+template <int ML>
+__device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<ML>& top, int qi, int k, int lane) {
+  if (p.xg.G > 0) {
+#pragma unroll
+    for (int m = 0; m < ML; ++m)
+      if (top.r[m] != kEmptyRow) top.r[m] += (uint32_t)p.row_base;   // global rows < 2^32 (checked on the host)
+    xchg_push(p.xg, top, p.xg.slot0 + qi, k, lane);
+    xchg_wait_merge(p.xg, top, p.xg.slot0 + qi, k, lane);
+  }
+  const int64_t add = p.xg.G > 0 ? 0 : p.row_base;
+  for (int e = lane; e < k; e += 32) {
+#pragma unroll
+    for (int m = 0; m < ML; ++m)
+      if ((e >> 5) == m) {
+        p.out_s[(size_t)qi * k + e] = top.s[m];
+        p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + add;
+      }
+  }
+}
 
 template <typename T>
 struct Elem;
@@ -254,15 +280,7 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKe
   if (warp == 0) {
     top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
     if (gridDim.x == 1) {
-      // single CTA: this is already the answer
-      for (int e = lane; e < k; e += 32) {
-#pragma unroll
-        for (int m = 0; m < ML; ++m)
-          if ((e >> 5) == m) {
-            p.out_s[(size_t)qi * k + e] = top.s[m];
-            p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + p.row_base;
-          }
-      }
+      emit_result<ML>(p, top, qi, k, lane);   // single CTA: this is already the shard's answer
     } else {
       top.store(p.part_s + pbase, p.part_r + pbase, k, lane);
       __threadfence();
@@ -291,15 +309,8 @@ __global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKe
   __syncthreads();
   if (warp == 0) {
     top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
-    for (int e = lane; e < k; e += 32) {
-#pragma unroll
-      for (int m = 0; m < ML; ++m)
-        if ((e >> 5) == m) {
-          p.out_s[(size_t)qi * k + e] = top.s[m];
-          p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + p.row_base;
-        }
-    }
     if (lane == 0) p.tickets[qi] = 0;  // ready for the next launch
+    emit_result<ML>(p, top, qi, k, lane);
   }
 }
 
@@ -354,6 +365,7 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.dim = a.dim;
   p.ld_bytes = (int)a.ld_bytes;
   p.k = a.k;
+  p.xg = a.xg;
   p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
   const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;
   int stages = (kSmemBudget - fixed) / p.stage_stride;

@@ -211,6 +211,66 @@ class DeviceIndex:
                                             G, B, k, _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
         return out_scores, out_rows
 
+    # -- peer exchange (row-sharded collection) --------------------------
+    def exchange_create(self, world_size: int, rank: int, b_max: int = 1024, k_max: int = 32) -> bytes:
+        """Allocate this shard's exchange buffer; returns the 64-byte CUDA IPC handle to publish."""
+        N.check(self._lib.vs_exchange_create(self._h, int(world_size), int(rank), int(b_max), int(k_max)))
+        h = (C.c_ubyte * 64)()
+        N.check(self._lib.vs_exchange_ipc_handle(self._h, h))
+        return bytes(h)
+
+    def exchange_local_ptr(self) -> int:
+        return int(self._lib.vs_exchange_local_ptr(self._h) or 0)
+
+    def exchange_attach(self, ipc_handles: Optional[Sequence[bytes]] = None,
+                        peer_ptrs: Optional[Sequence[int]] = None):
+        """Map the peers' buffers: ``ipc_handles[g]`` (other processes) or ``peer_ptrs[g]`` (same process)."""
+        hb = None
+        if ipc_handles is not None:
+            blob = b"".join(bytes(h) if h else b"\0" * 64 for h in ipc_handles)
+            hb = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        pp = None
+        if peer_ptrs is not None:
+            pp = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) if p else C.c_void_p(None) for p in peer_ptrs])
+        N.check(self._lib.vs_exchange_attach(self._h, hb, pp))
+
+    def query_sharded_dev(self, q, k: int, out_scores=None, out_rows=None,
+                          require_bits: Optional[Sequence[int]] = None, mode: str = "auto", stream=None):
+        """Like ``query_dev`` but returns the GLOBAL top-k over all shards on every rank: the exchange
+        over NVLink peer memory is fused into the query kernel (vs_query_topk_sharded_dev)."""
+        import torch
+        if q.dim() == 1:
+            q = q[None]
+        if not q.is_cuda or q.dtype != torch.float32 or q.shape[1] != self.dim:
+            raise ValueError("queries must be a CUDA float32 [B, dim] tensor")
+        q = q.contiguous()
+        B = q.shape[0]
+        if out_scores is None:
+            out_scores = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        if out_rows is None:
+            out_rows = torch.empty((B, k), dtype=torch.int64, device=q.device)
+        st = stream if stream is not None else torch.cuda.current_stream(q.device)
+        N.check(self._lib.vs_query_topk_sharded_dev(self._h, _ptr(q), B, int(k), _bits_array(require_bits),
+                                                    _MODES[mode], _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
+        return out_scores, out_rows
+
+    def exchange_merge_dev(self, cand_scores, cand_rows, out_scores=None, out_rows=None, stream=None):
+        """The exchange kernel alone (vs_exchange_merge_dev): this rank's [B,k] candidates (global
+        rows) are pushed into every peer's buffer, flags are exchanged, and the G lists are merged."""
+        import torch
+        B, k = cand_scores.shape
+        if out_scores is None:
+            out_scores = torch.empty((B, k), dtype=torch.float32, device=cand_scores.device)
+        if out_rows is None:
+            out_rows = torch.empty((B, k), dtype=torch.int64, device=cand_scores.device)
+        st = stream if stream is not None else torch.cuda.current_stream(cand_scores.device)
+        N.check(self._lib.vs_exchange_merge_dev(self._h, _ptr(cand_scores.contiguous()), _ptr(cand_rows.contiguous()),
+                                                B, k, _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
+        return out_scores, out_rows
+
+    def exchange_error(self) -> int:
+        return int(self._lib.vs_exchange_error(self._h))
+
     # -- filter sweep / dedup -----------------------------------------------------------------
     def filter_words(self) -> int:
         return int(self._lib.vs_filter_words(self._h))

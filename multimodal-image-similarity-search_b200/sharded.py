@@ -1,9 +1,13 @@
 """Row-sharded search across the GPUs of one box: one process per GPU (torch.distributed).
 
 SURVEY.md section 8(e): the corpus is split into contiguous row ranges, every rank scans its
-shard for the (replicated) queries, the per-rank ``[B, k]`` candidates are exchanged with ONE
-small all-gather (``B*k*12`` bytes per rank over NVLink/NVSwitch with NCCL) and merged on every
-rank by the K5 kernel, so all ranks end with the same global answer.
+shard for the (replicated) queries, the per-rank ``[B, k]`` candidates are exchanged and merged on
+every rank, so all ranks end with the same global answer.  Two exchanges:
+
+* ``exchange="nccl"``  -- one small all-gather pair (``B*k*12`` bytes per rank) + the K5 merge kernel;
+* ``exchange="p2p"``   -- ONE fused kernel (``vs_exchange_merge_dev``): each rank stores its candidates
+  straight into every peer's symmetric-memory buffer over NVLink/NVSwitch (P2P stores), signals
+  per-query flags, waits for the peers' flags and merges.  No NCCL call on the query path.
 
 The searcher is backend-agnostic on purpose: ``local_topk`` and ``merge`` are injected, so the
 partitioning + exchange logic is testable with world_size-2 ``gloo`` on CPU (tests inject the
@@ -21,27 +25,67 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+class PeerExchange:
+    """Exchange buffers of ``vs_query_topk_sharded_dev`` for one process-per-GPU group: every rank
+    allocates its buffer in the library, the CUDA IPC handles are all-gathered once at set-up
+    (host side), and each rank maps its peers' buffers.  Nothing but kernels runs per query."""
+
+    def __init__(self, index, group=None, b_max: int = 1024, k_max: int = 32):
+        import torch.distributed as dist
+        self.index, self.b_max, self.k_max = index, int(b_max), int(k_max)
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world_size > 8:
+            raise ValueError("the peer exchange supports at most 8 ranks (one NVSwitch domain)")
+        mine = index.exchange_create(self.world_size, self.rank, self.b_max, self.k_max)
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, mine, group=group)       # also orders "every buffer is zeroed"
+        index.exchange_attach(ipc_handles=handles)
+        dist.barrier(group=group)                                # every rank has mapped every buffer
+
+    def search(self, q, k: int, mode: str = "auto", out_scores=None, out_rows=None):
+        return self.index.query_sharded_dev(q, k, out_scores=out_scores, out_rows=out_rows, mode=mode)
+
+    def exchange_merge(self, s, r, out_scores=None, out_rows=None):
+        return self.index.exchange_merge_dev(s, r, out_scores=out_scores, out_rows=out_rows)
+
+
 class ShardedSearcher:
     """``local_topk(q, k) -> (scores [B,k] f32, rows [B,k] i64 GLOBAL rows, -1 = empty)`` and
     ``merge(cand_scores [G,B,k], cand_rows [G,B,k]) -> (scores [B,k], rows [B,k])`` operate on
     torch tensors living on the device the process group communicates on."""
 
-    def __init__(self, local_topk: Callable, merge: Callable, group=None):
+    def __init__(self, local_topk: Callable, merge: Callable, group=None, peer_exchange: Optional[PeerExchange] = None,
+                 mode: str = "auto"):
         import torch.distributed as dist
         self._dist = dist
         self.local_topk, self.merge, self.group = local_topk, merge, group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.peer_exchange, self.mode = peer_exchange, mode
         self._gs = self._gr = None
 
+    @property
+    def exchange(self) -> str:
+        return "p2p" if self.peer_exchange is not None else "nccl"
+
     @classmethod
-    def for_index(cls, index, group=None, mode: str = "auto"):
-        """Product wiring: K1/K2 for the local scan, K5 for the merge (all CUDA)."""
+    def for_index(cls, index, group=None, mode: str = "auto", exchange: str = "nccl", b_max: int = 1024,
+                  k_max: int = 32):
+        """Product wiring: K1/K2 for the local scan, K5 (or the fused peer exchange) for the merge."""
+        import torch.distributed as dist
+        px = None
+        if exchange == "p2p" and dist.is_initialized() and dist.get_world_size(group) > 1:
+            px = PeerExchange(index, group, b_max, k_max)
+        elif exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
         return cls(lambda q, k: index.query_dev(q, k, mode=mode),
-                   lambda cs, cr: index.merge_dev(cs, cr), group)
+                   lambda cs, cr: index.merge_dev(cs, cr), group, px, mode)
 
     def search(self, q, k: int):
         import torch
+        if self.peer_exchange is not None and self.world_size > 1 and k <= self.peer_exchange.k_max:
+            return self.peer_exchange.search(q, k, self.mode)    # scan/tcgen05 kernel + fused exchange
         s, r = self.local_topk(q, k)
         if self.world_size == 1:
             return s, r

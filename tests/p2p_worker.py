@@ -1,0 +1,73 @@
+"""Worker of tests/test_gpu_exchange.py::test_two_gpu_processes_ipc_exchange (one process per GPU,
+launched by torch.distributed.run): fused peer exchange == NCCL all-gather + merge == oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mmiss_b200 as M  # noqa: E402
+from oracle import cosine_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(0)
+    n, d = 200_000, 512
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[n - 1] = X[7]
+    Q = np.concatenate([rng.standard_normal((95, d)).astype(np.float32), X[7:8]])
+    lo, hi = M.shard_bounds(n, world, rank)
+    for dtype, tol in (("bf16", 2e-3), ("f32", 1e-5)):
+        ix = M.DeviceIndex(d, dtype, device=local, row_base=lo)
+        ix.add(X[lo:hi])
+        p2p = M.ShardedSearcher.for_index(ix, mode="scan", exchange="p2p", b_max=128, k_max=32)
+        nccl = M.ShardedSearcher.for_index(ix, mode="scan", exchange="nccl")
+        assert p2p.exchange == "p2p" and nccl.exchange == "nccl"
+        qd = torch.from_numpy(Q).to(dev)
+        full = O.cosine_scores(Q, X, corpus_dtype=dtype)
+        for k in (10, 32):
+            for B in (1, 7, 64, 96):
+                for rep in range(3):
+                    s, r = p2p.search(qd[:B], k)
+                    s2, r2 = nccl.search(qd[:B], k)
+                    torch.cuda.synchronize()
+                    assert ix.exchange_error() == 0
+                    assert torch.equal(r, r2) and torch.equal(s, s2), (dtype, k, B, rep)
+                sn, rn = s.cpu().numpy(), r.cpu().numpy()
+                for b in range(B):
+                    ok, why = O.topk_matches(sn[b], rn[b], full[b], k, tol)
+                    assert ok, why
+        # single-query launches back to back, no host synchronisation in between
+        outs = [p2p.search(qd[b:b + 1], 10) for b in range(32)]
+        torch.cuda.synchronize()
+        for b, (s, r) in enumerate(outs):
+            ok, why = O.topk_matches(s[0].cpu().numpy(), r[0].cpu().numpy(), full[b], 10, tol)
+            assert ok, why
+        if dtype == "bf16":
+            pt = M.ShardedSearcher(p2p.local_topk, p2p.merge, None, p2p.peer_exchange, "tensor")
+            s, r = pt.search(qd, 10)
+            torch.cuda.synchronize()
+            fullr = O.cosine_scores(Q, X, corpus_dtype="bf16", round_queries=True)
+            for b in range(Q.shape[0]):
+                ok, why = O.topk_matches(s[b].cpu().numpy(), r[b].cpu().numpy(), fullr[b], 10, tol)
+                assert ok, why
+        got = [torch.zeros_like(r) for _ in range(world)]
+        dist.all_gather(got, r)
+        assert all(torch.equal(got[0], g) for g in got)
+        dist.barrier()
+        ix.close()
+    if rank == 0:
+        print("p2p worker ok")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
