@@ -655,6 +655,23 @@ int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
   CU(cudaMemset(ix->xc.local, 0, bytes));
   CU(ix->d_err.reserve(16));
   CU(cudaMemset(ix->d_err.p, 0, 16));
+  // no allocation on the sharded query path: a cudaFree there would synchronise the device while a
+  // peer may be spinning on this rank's push.  Reserve every scratch buffer for (B_max, k_max) now.
+  CU(ix->d_xs.reserve((size_t)B_max * k_max * sizeof(float)));
+  CU(ix->d_xr.reserve((size_t)B_max * k_max * sizeof(int64_t)));
+  CU(ix->d_part_s.reserve((size_t)kScanBatch * ix->sm_count * k_max * sizeof(float)));
+  CU(ix->d_part_r.reserve((size_t)kScanBatch * ix->sm_count * k_max * sizeof(uint32_t)));
+  if (ix->tickets_n < (size_t)kScanBatch) {
+    CU(ix->d_tickets.reserve(kScanBatch * sizeof(unsigned int)));
+    CU(cudaMemset(ix->d_tickets.p, 0, ix->d_tickets.bytes));
+    ix->tickets_n = kScanBatch;
+  }
+  if (ix->dtype == VS_BF16 && ix->dim % 8 == 0 && ix->dim <= 768 && vs::tensor_path_available()) {
+    const int64_t rows_hint = ix->cap > ix->n ? ix->cap : ix->n;
+    const int kt = k_max < vs::kMaxTensorK ? k_max : vs::kMaxTensorK;
+    CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B_max, ix->dim, kt, ix->sm_count, rows_hint > 0 ? rows_hint : 1)));
+  }
+  CU(vs::preload_exchange_kernels());
   CU(cudaDeviceSynchronize());
   ix->xc.G = G;
   ix->xc.rank = rank;
@@ -752,26 +769,33 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
   if (rc) return rc;
   cudaStream_t st = pick_stream(ix, stream);
   if (ix->xc.G == 1) return query_dev_locked(ix, q_dev, B, k, require_bits, mode, out_scores_dev, out_rows_dev, st);
-  // try the fused form first: the local result never leaves the scan kernel
-  CU(ix->d_xs.reserve((size_t)B * k * sizeof(float)));
-  CU(ix->d_xr.reserve((size_t)B * k * sizeof(int64_t)));
-  bool fused = false;
   int path = mode;
   if (path == VS_Q_AUTO)
     path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
             vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
-  if (path == VS_Q_SCAN && ix->n > 0 && B <= kScanBatch) {
+  // fused form: the shard's result never leaves the scan kernel (one launch, exchange inside)
+  if (path == VS_Q_SCAN && ix->n > 0 && B <= kScanBatch && B <= ix->xc.Bmax) {
+    bool fused = false;
     rc = query_dev_locked(ix, q_dev, B, k, require_bits, VS_Q_SCAN, out_scores_dev, out_rows_dev, st, &fused);
     if (rc) return rc;
     if (fused) return VS_OK;
-    // (a filter without bits produced an all-empty local result in out_*: exchange it below)
+    // (a filter nobody carries bits for produced an all-empty local result in out_*: exchange it)
     CU(cudaMemcpyAsync(ix->d_xs.p, out_scores_dev, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(ix->d_xr.p, out_rows_dev, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  } else {
-    rc = query_dev_locked(ix, q_dev, B, k, require_bits, path, (float*)ix->d_xs.p, (int64_t*)ix->d_xr.p, st);
+    return exchange_chunks(ix, (const float*)ix->d_xs.p, (const int64_t*)ix->d_xr.p, B, k, out_scores_dev, out_rows_dev, st);
+  }
+  // general form, in chunks of B_max queries: local query (K1 batches or K2) into scratch, then the
+  // exchange kernel; the scratch was reserved by vs_exchange_create
+  for (int b0 = 0; b0 < B; b0 += ix->xc.Bmax) {
+    const int nb = B - b0 < ix->xc.Bmax ? B - b0 : ix->xc.Bmax;
+    rc = query_dev_locked(ix, q_dev + (size_t)b0 * ix->dim, nb, k, require_bits, path, (float*)ix->d_xs.p,
+                          (int64_t*)ix->d_xr.p, st);
+    if (rc) return rc;
+    rc = exchange_chunks(ix, (const float*)ix->d_xs.p, (const int64_t*)ix->d_xr.p, nb, k, out_scores_dev + (size_t)b0 * k,
+                         out_rows_dev + (size_t)b0 * k, st);
     if (rc) return rc;
   }
-  return exchange_chunks(ix, (const float*)ix->d_xs.p, (const int64_t*)ix->d_xr.p, B, k, out_scores_dev, out_rows_dev, st);
+  return VS_OK;
 }
 
 int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B, int k,

@@ -59,6 +59,7 @@ cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k
                          cudaStream_t st);
 // the exchange kernel alone: [B][k] candidates (global rows, <0 empty) of this rank -> global [B][k]
 size_t exchange_bytes(int Bmax, int kmax, int G);
+cudaError_t preload_exchange_kernels();
 cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
                                   int64_t* out_r, int sm_count, cudaStream_t st);
 // general form: candidates [G][Bstride][kin] -> [B][kout]

@@ -278,6 +278,18 @@ __global__ void __launch_bounds__(kXchgWarps * 32) exchange_merge_kernel(const f
   }
 }
 
+// CUDA loads kernels lazily and a first launch may synchronise the context.  When several shards
+// live in ONE process (tests, single-GPU multi-handle use) a peer's kernel may already be spinning
+// on this shard's push at that moment, so everything the sharded path can launch besides the scan
+// kernel itself is loaded up front (called by vs_exchange_create).
+cudaError_t preload_exchange_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<1>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<4>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fill_empty_kernel);
+  return e;
+}
+
 cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
                                   int64_t* out_r, int sm_count, cudaStream_t st) {
   if (x.G <= 0 || x.G > kMaxPeers || x.rank < 0 || x.rank >= x.G || B <= 0 || x.slot0 + B > x.Bmax || k <= 0 ||
