@@ -277,8 +277,8 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
   const bool large_k = k > vs::kMaxFusedK;
   const int step = large_k ? 4 : kScanBatch;
   if (!large_k) {
-    CU(ix->d_part_s.reserve((size_t)step * ix->sm_count * k * sizeof(float)));
-    CU(ix->d_part_r.reserve((size_t)step * ix->sm_count * k * sizeof(uint32_t)));
+    CU(ix->d_part_s.reserve((size_t)step * ix->sm_count * vs::kScanMaxCtasPerSm * k * sizeof(float)));
+    CU(ix->d_part_r.reserve((size_t)step * ix->sm_count * vs::kScanMaxCtasPerSm * k * sizeof(uint32_t)));
   } else {
     CU(ix->d_scores.reserve((size_t)step * ix->n * sizeof(float)));
     CU(ix->d_select.reserve(vs::select_workspace_bytes(step)));
@@ -659,8 +659,8 @@ int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
   // peer may be spinning on this rank's push.  Reserve every scratch buffer for (B_max, k_max) now.
   CU(ix->d_xs.reserve((size_t)B_max * k_max * sizeof(float)));
   CU(ix->d_xr.reserve((size_t)B_max * k_max * sizeof(int64_t)));
-  CU(ix->d_part_s.reserve((size_t)kScanBatch * ix->sm_count * k_max * sizeof(float)));
-  CU(ix->d_part_r.reserve((size_t)kScanBatch * ix->sm_count * k_max * sizeof(uint32_t)));
+  CU(ix->d_part_s.reserve((size_t)kScanBatch * ix->sm_count * vs::kScanMaxCtasPerSm * k_max * sizeof(float)));
+  CU(ix->d_part_r.reserve((size_t)kScanBatch * ix->sm_count * vs::kScanMaxCtasPerSm * k_max * sizeof(uint32_t)));
   if (ix->tickets_n < (size_t)kScanBatch) {
     CU(ix->d_tickets.reserve(kScanBatch * sizeof(unsigned int)));
     CU(cudaMemset(ix->d_tickets.p, 0, ix->d_tickets.bytes));

@@ -11,6 +11,7 @@ constexpr int kMaskWords = 4;
 constexpr int kMaxFusedK = 128;   // register-list top-k limit of the fused scan kernel
 constexpr int kMaxTensorK = 32;   // per-thread register list limit of the tcgen05 top-k epilogue
 constexpr int kMaxK = 1024;
+constexpr int kScanMaxCtasPerSm = 4;   // the partial-list workspace is sized for this many CTAs per SM
 
 void count_launch(int n = 1);
 

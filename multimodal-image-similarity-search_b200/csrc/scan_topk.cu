@@ -27,7 +27,13 @@
 namespace vs {
 
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 220 * 1024;
+// Shared memory per CTA.  Deliberately about a third of the SM: two CTAs fit on one SM, so with
+// programmatic dependent launch the NEXT query's CTAs are already resident and streaming while this
+// query's CTAs run their merge/exchange tails -- the HBM pipe never drains between queries
+// (profiles/r01_scan_ab.md: 6.4 -> 7.3 TB/s on back-to-back 10M x 512 bf16 scans).
+constexpr int kSmemBudget = 76 * 1024;
+constexpr int kCtasPerSm = 2;
+constexpr int kSmemMax = 220 * 1024;
 
 // rows per consumer warp per tile, chosen so a stage (W warps x U rows x pitch) is <= 32 KB
 __host__ __device__ constexpr int rows_per_warp(int cpl, int w) {
@@ -119,7 +125,7 @@ __device__ __forceinline__ bool mask_ok(const uint64_t* mask, uint32_t row, cons
 
 // M == 0: materialise scores (large-k path) instead of keeping lists.
 template <typename T, int CPL, int M, int W, bool FULL>
-__global__ void __launch_bounds__((W + 1) * 32, 1) scan_topk_kernel(const ScanKernelParams p) {
+__global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) scan_topk_kernel(const ScanKernelParams p) {
   constexpr int kConsumerWarps = W;
   constexpr int EPC = Elem<T>::kPerChunk;
   constexpr int U = rows_per_warp(CPL, W);
@@ -368,7 +374,19 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.xg = a.xg;
   p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
   const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;
-  int stages = (kSmemBudget - fixed) / p.stage_stride;
+  // tuning knobs for A/B runs on the box (tools/bench_scan.py); the defaults are the product values
+  static const int smem_budget = [] {
+    const char* v = getenv("VS_SCAN_SMEM_KB");
+    const int kb = v ? atoi(v) : 0;
+    return kb >= 16 && kb <= 220 ? kb * 1024 : kSmemBudget;
+  }();
+  static const int ctas_per_sm = [] {
+    const char* v = getenv("VS_SCAN_CTAS_PER_SM");
+    const int c = v ? atoi(v) : 0;
+    return c >= 1 && c <= 4 ? c : kCtasPerSm;
+  }();
+  int stages = (smem_budget - fixed) / p.stage_stride;
+  if (stages < 3) stages = (kSmemMax - fixed) / p.stage_stride < 3 ? (kSmemMax - fixed) / p.stage_stride : 3;  // wide rows
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidValue;
   p.stages = stages;
@@ -376,7 +394,7 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   auto kern = scan_topk_kernel<T, CPL, M, W, FULL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int gx = a.grid_x > 0 ? a.grid_x : sm_count;
+  int gx = (a.grid_x > 0 ? a.grid_x : sm_count) * ctas_per_sm;
   if ((uint32_t)gx > p.n_tiles) gx = (int)p.n_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, a.B, 1);
