@@ -256,9 +256,10 @@ def run_ours(args):
         if timed:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        if p2p:                                  # scan + NVLink exchange + merge fused: one kernel per query
+        if p2p:        # every scan kernel pushes its top-k to all peers over NVLink; one collect kernel per step
+            ix.exchange_begin()
             for i in range(Q):
-                ix.query_sharded_dev(q_dev[i:i + 1], k, out_scores=out_s[i:i + 1], out_rows=out_r[i:i + 1], mode="scan")
+                ix.query_push_dev(q_dev[i:i + 1], k, i, mode="scan")
         else:
             for i in range(Q):                   # Q independent single-query scans (one kernel each)
                 ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan")
@@ -266,7 +267,7 @@ def run_ours(args):
             e1.record()
             scan_ev.append((e0, e1))
         if p2p:
-            return out_s, out_r
+            return ix.exchange_collect_dev(Q, k, out_scores=out_s, out_rows=out_r)
         if G > 1:
             dist.all_gather_into_tensor(gath_s, cand_s)
             dist.all_gather_into_tensor(gath_r, cand_r)

@@ -154,6 +154,16 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
 int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B,
                           int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
 int vs_exchange_error(vs_index_t* ix);
+/* Deferred form for a stream of independent queries (throughput mode): vs_exchange_begin opens a
+ * new exchange; each vs_query_topk_push_dev runs the local query and pushes its candidates into
+ * slots [slot0, slot0+B) of every peer (fused into the scan kernel as above, no waiting); ONE
+ * vs_exchange_collect_dev(B_total, k) then waits for and merges slots [0, B_total) -> [B_total, k].
+ * The ranks meet once per batch instead of once per query.  Same k for every push of an exchange. */
+int vs_exchange_begin(vs_index_t* ix);
+int vs_query_topk_push_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits,
+                           int mode, int slot0, void* stream);
+int vs_exchange_collect_dev(vs_index_t* ix, int B, int k, float* out_scores_dev, int64_t* out_rows_dev,
+                            void* stream);
 
 /* ---- filter sweep (BASELINE config 4; CLIP-side analogue of process_filter_on_all_images,
  *      backend/app/main.py:939-1056): prompts [F, dim] float32 (host or device) -> bit mask

@@ -201,8 +201,9 @@ cudaStream_t pick_stream(vs_index* ix, void* stream) { return stream ? (cudaStre
 // queries per scan launch (bounds the partial-list workspace)
 constexpr int kScanBatch = 64;
 
-// fills the kernel-side exchange descriptor for the NEXT exchange (advances the epoch)
-vs::XchgParams next_exchange(vs_index* ix, int slot0) {
+// kernel-side exchange descriptor for the CURRENT epoch; `advance` starts a new exchange first
+vs::XchgParams make_exchange(vs_index* ix, int slot0, bool advance, bool push_only) {
+  if (advance && ++ix->xc.epoch == 0) ix->xc.epoch = 2;   // 0 is the "never written" flag value; keep the parity sequence
   vs::XchgParams x = {};
   for (int g = 0; g < ix->xc.G; ++g) x.peers[g] = static_cast<unsigned char*>(ix->xc.peers[g]);
   x.err = (unsigned int*)ix->d_err.p;
@@ -211,15 +212,16 @@ vs::XchgParams next_exchange(vs_index* ix, int slot0) {
   x.Bmax = ix->xc.Bmax;
   x.kmax = ix->xc.kmax;
   x.slot0 = slot0;
-  if (++ix->xc.epoch == 0) ix->xc.epoch = 2;   // 0 is the "never written" flag value; keep the parity sequence
   x.epoch = ix->xc.epoch;
+  x.push_only = push_only ? 1 : 0;
   return x;
 }
 
 // `fused_exchange`: when non-null and the query takes the fused scan path in ONE launch, the
-// exchange is done by the scan kernel itself and *fused_exchange is set to true.
+// exchange (or, with push_slot0 >= 0, only the push into slots [push_slot0, +B) of the current
+// epoch) is done by the scan kernel itself and *fused_exchange is set to true.
 int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint64_t* req, int mode, float* out_s,
-                     int64_t* out_r, cudaStream_t st, bool* fused_exchange = nullptr) {
+                     int64_t* out_r, cudaStream_t st, bool* fused_exchange = nullptr, int push_slot0 = -1) {
   if (fused_exchange) *fused_exchange = false;
   if (B <= 0) return VS_OK;
   if (k <= 0 || k > vs::kMaxK) return fail(VS_ERR_ARG, "k=%d out of range [1,%d]", k, vs::kMaxK);
@@ -311,7 +313,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     a.out_r = out_r + (size_t)b0 * k;
     a.scores_full = large_k ? (float*)ix->d_scores.p : nullptr;
     if (fused_exchange && !large_k && B <= step) {
-      a.xg = next_exchange(ix, 0);
+      a.xg = push_slot0 >= 0 ? make_exchange(ix, push_slot0, false, true) : make_exchange(ix, 0, true, false);
       *fused_exchange = true;
     }
     CU(vs::launch_scan(a, ix->sm_count, st));
@@ -751,7 +753,7 @@ int exchange_chunks(vs_index* ix, const float* cs, const int64_t* cr, int B, int
                     cudaStream_t st) {
   for (int b0 = 0; b0 < B; b0 += ix->xc.Bmax) {
     const int nb = B - b0 < ix->xc.Bmax ? B - b0 : ix->xc.Bmax;
-    const vs::XchgParams x = next_exchange(ix, 0);
+    const vs::XchgParams x = make_exchange(ix, 0, true, false);
     CU(vs::launch_exchange_merge(cs + (size_t)b0 * k, cr + (size_t)b0 * k, x, nb, k, out_s + (size_t)b0 * k,
                                  out_r + (size_t)b0 * k, ix->sm_count, st));
   }
@@ -795,6 +797,64 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
                          out_rows_dev + (size_t)b0 * k, st);
     if (rc) return rc;
   }
+  return VS_OK;
+}
+
+int vs_exchange_begin(vs_index_t* ix) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!ix->xc.local || !ix->xc.attached) return fail(VS_ERR_ARG, "exchange not created/attached");
+  if (++ix->xc.epoch == 0) ix->xc.epoch = 2;
+  return VS_OK;
+}
+
+int vs_query_topk_push_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits, int mode,
+                           int slot0, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B <= 0 || !q_dev) return fail(VS_ERR_ARG, "bad B or NULL buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  int rc = exchange_ready(ix, k);
+  if (rc) return rc;
+  if (ix->xc.epoch == 0) return fail(VS_ERR_ARG, "vs_exchange_begin has not been called");
+  if (slot0 < 0 || slot0 + B > ix->xc.Bmax) return fail(VS_ERR_ARG, "slots [%d,%d) exceed B_max=%d", slot0, slot0 + B, ix->xc.Bmax);
+  cudaStream_t st = pick_stream(ix, stream);
+  int path = mode;
+  if (path == VS_Q_AUTO)
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+            vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
+  float* xs = (float*)ix->d_xs.p;
+  int64_t* xr = (int64_t*)ix->d_xr.p;
+  if (path == VS_Q_SCAN && ix->n > 0 && B <= kScanBatch) {
+    bool fused = false;
+    rc = query_dev_locked(ix, q_dev, B, k, require_bits, VS_Q_SCAN, xs, xr, st, &fused, slot0);
+    if (rc) return rc;
+    if (fused) return VS_OK;          // the scan kernel's last CTA pushed the candidates
+  } else {
+    rc = query_dev_locked(ix, q_dev, B, k, require_bits, path, xs, xr, st);
+    if (rc) return rc;
+  }
+  CU(vs::launch_exchange_merge(xs, xr, make_exchange(ix, slot0, false, true), B, k, nullptr, nullptr, ix->sm_count, st, 1));
+  return VS_OK;
+}
+
+int vs_exchange_collect_dev(vs_index_t* ix, int B, int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B <= 0 || !out_scores_dev || !out_rows_dev) return fail(VS_ERR_ARG, "bad B or NULL buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  int rc = exchange_ready(ix, k);
+  if (rc) return rc;
+  if (B > ix->xc.Bmax) return fail(VS_ERR_ARG, "B=%d exceeds B_max=%d", B, ix->xc.Bmax);
+  cudaStream_t st = pick_stream(ix, stream);
+  if (ix->last_stream_valid && ix->last_stream != st) {
+    CU(cudaEventRecord(ix->ev, ix->last_stream));
+    CU(cudaStreamWaitEvent(st, ix->ev, 0));
+  }
+  ix->last_stream = st;
+  ix->last_stream_valid = true;
+  CU(vs::launch_exchange_merge(nullptr, nullptr, make_exchange(ix, 0, false, false), B, k, out_scores_dev, out_rows_dev,
+                               ix->sm_count, st, 2));
   return VS_OK;
 }
 

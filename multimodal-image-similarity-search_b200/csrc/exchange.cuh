@@ -9,6 +9,10 @@
 //               every rank,
 //   3. wait   : ld.acquire.sys spin on the G LOCAL flags of the slot (bounded, sets *err),
 //   4. merge  : merges the G lists that now sit in LOCAL memory into its register top-k list.
+// Steps 3+4 may be deferred: a batch of independent queries pushes into distinct slots of ONE epoch
+// (push_only) and a single collect kernel waits for + merges all of them, so the ranks meet once
+// per batch instead of once per query (per-query rendezvous makes every query as slow as the
+// momentarily slowest GPU).
 // The buffer has two halves selected by epoch parity.  A rank can be at most one exchange ahead
 // of any peer: completing exchange e needs every peer's flag of e, and a peer raises it only after
 // its own exchange e-1 finished (stream order / griddepcontrol.wait), so when half (e & 1) is
@@ -29,6 +33,7 @@ struct XchgParams {
   int Bmax, kmax;
   int slot0;                         // slot of query 0 of this launch
   uint32_t epoch;
+  int push_only;                     // 1: steps 1+2 only; a later collect kernel does 3+4 for the whole epoch
 };
 
 struct XchgLayout {

@@ -61,8 +61,9 @@ cudaError_t launch_merge(const float* cs, const int64_t* cr, int G, int B, int k
 // the exchange kernel alone: [B][k] candidates (global rows, <0 empty) of this rank -> global [B][k]
 size_t exchange_bytes(int Bmax, int kmax, int G);
 cudaError_t preload_exchange_kernels();
+// what: 3 = push + wait + merge (one exchange), 1 = push only, 2 = wait + merge only (deferred collect)
 cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
-                                  int64_t* out_r, int sm_count, cudaStream_t st);
+                                  int64_t* out_r, int sm_count, cudaStream_t st, int what = 3);
 // general form: candidates [G][Bstride][kin] -> [B][kout]
 cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
                             float* out_s, int64_t* out_r, cudaStream_t st);

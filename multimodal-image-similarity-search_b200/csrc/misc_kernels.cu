@@ -252,7 +252,8 @@ __device__ __forceinline__ void load_candidates(WarpTopK<M>& top, const float* c
   }
 }
 
-template <int M>
+// PUSH: candidates of this rank -> every peer's buffer + flags.  COLLECT: wait + merge + write.
+template <int M, bool PUSH, bool COLLECT>
 __global__ void __launch_bounds__(kXchgWarps * 32) exchange_merge_kernel(const float* __restrict__ cs,
                                                                          const int64_t* __restrict__ cr, XchgParams x, int B,
                                                                          int k, float* __restrict__ out_s,
@@ -261,18 +262,22 @@ __global__ void __launch_bounds__(kXchgWarps * 32) exchange_merge_kernel(const f
   const int w0 = blockIdx.x * kXchgWarps + (threadIdx.x >> 5);
   const int nw = gridDim.x * kXchgWarps;
   WarpTopK<M> top;
-  for (int b = w0; b < B; b += nw) {
-    load_candidates(top, cs + (size_t)b * k, cr + (size_t)b * k, k, lane);
-    xchg_push(x, top, x.slot0 + b, k, lane);
+  if constexpr (PUSH) {
+    for (int b = w0; b < B; b += nw) {
+      load_candidates(top, cs + (size_t)b * k, cr + (size_t)b * k, k, lane);
+      xchg_push(x, top, x.slot0 + b, k, lane);
+    }
   }
-  for (int b = w0; b < B; b += nw) {
-    xchg_wait_merge(x, top, x.slot0 + b, k, lane);
+  if constexpr (COLLECT) {
+    for (int b = w0; b < B; b += nw) {
+      xchg_wait_merge(x, top, x.slot0 + b, k, lane);
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      const int p = m * 32 + lane;
-      if (p < k) {
-        out_s[(size_t)b * k + p] = top.s[m];
-        out_r[(size_t)b * k + p] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m];
+      for (int m = 0; m < M; ++m) {
+        const int p = m * 32 + lane;
+        if (p < k) {
+          out_s[(size_t)b * k + p] = top.s[m];
+          out_r[(size_t)b * k + p] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m];
+        }
       }
     }
   }
@@ -284,23 +289,34 @@ __global__ void __launch_bounds__(kXchgWarps * 32) exchange_merge_kernel(const f
 // kernel itself is loaded up front (called by vs_exchange_create).
 cudaError_t preload_exchange_kernels() {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<1>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<4>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<1, true, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<4, true, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<1, true, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<4, true, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<1, false, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, exchange_merge_kernel<4, false, true>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fill_empty_kernel);
   return e;
 }
 
+// what: 3 = push + collect (one exchange), 1 = push only, 2 = collect only
 cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
-                                  int64_t* out_r, int sm_count, cudaStream_t st) {
-  if (x.G <= 0 || x.G > kMaxPeers || x.rank < 0 || x.rank >= x.G || B <= 0 || x.slot0 + B > x.Bmax || k <= 0 ||
-      k > x.kmax || k > kMaxFusedK)
+                                  int64_t* out_r, int sm_count, cudaStream_t st, int what) {
+  if (x.G <= 0 || x.G > kMaxPeers || x.rank < 0 || x.rank >= x.G || B <= 0 || x.slot0 < 0 || x.slot0 + B > x.Bmax ||
+      k <= 0 || k > x.kmax || k > kMaxFusedK || what < 1 || what > 3)
     return cudaErrorInvalidValue;
   int grid = (B + kXchgWarps - 1) / kXchgWarps;
   if (grid > sm_count) grid = sm_count;
-  if (k <= 32)
-    exchange_merge_kernel<1><<<grid, kXchgWarps * 32, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
-  else
-    exchange_merge_kernel<4><<<grid, kXchgWarps * 32, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+  const dim3 g(grid), b(kXchgWarps * 32);
+  if (k <= 32) {
+    if (what == 3) exchange_merge_kernel<1, true, true><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+    else if (what == 1) exchange_merge_kernel<1, true, false><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+    else exchange_merge_kernel<1, false, true><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+  } else {
+    if (what == 3) exchange_merge_kernel<4, true, true><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+    else if (what == 1) exchange_merge_kernel<4, true, false><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+    else exchange_merge_kernel<4, false, true><<<g, b, 0, st>>>(cs, cr, x, B, k, out_s, out_r);
+  }
   count_launch();
   return cudaGetLastError();
 }

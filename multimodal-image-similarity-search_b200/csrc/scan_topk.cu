@@ -75,6 +75,7 @@ __device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<
     for (int m = 0; m < ML; ++m)
       if (top.r[m] != kEmptyRow) top.r[m] += (uint32_t)p.row_base;   // global rows < 2^32 (checked on the host)
     xchg_push(p.xg, top, p.xg.slot0 + qi, k, lane);
+    if (p.xg.push_only) return;   // vs_exchange_collect_dev merges the whole epoch later
     xchg_wait_merge(p.xg, top, p.xg.slot0 + qi, k, lane);
   }
   const int64_t add = p.xg.G > 0 ? 0 : p.row_base;

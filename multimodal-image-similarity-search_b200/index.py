@@ -268,6 +268,36 @@ class DeviceIndex:
                                                 B, k, _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
         return out_scores, out_rows
 
+    def exchange_begin(self):
+        """Open a new deferred exchange (see ``query_push_dev`` / ``exchange_collect_dev``)."""
+        N.check(self._lib.vs_exchange_begin(self._h))
+
+    def query_push_dev(self, q, k: int, slot0: int, require_bits: Optional[Sequence[int]] = None,
+                       mode: str = "auto", stream=None):
+        """Local query + push of its candidates into slots [slot0, slot0+B) of every peer; no waiting."""
+        import torch
+        if q.dim() == 1:
+            q = q[None]
+        if not q.is_cuda or q.dtype != torch.float32 or q.shape[1] != self.dim:
+            raise ValueError("queries must be a CUDA float32 [B, dim] tensor")
+        q = q.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(q.device)
+        N.check(self._lib.vs_query_topk_push_dev(self._h, _ptr(q), q.shape[0], int(k), _bits_array(require_bits),
+                                                 _MODES[mode], int(slot0), _stream_ptr(st)))
+
+    def exchange_collect_dev(self, B: int, k: int, out_scores=None, out_rows=None, stream=None):
+        """Wait for and merge slots [0, B) of the open exchange -> global (scores [B,k], rows [B,k])."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if out_scores is None:
+            out_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        if out_rows is None:
+            out_rows = torch.empty((B, k), dtype=torch.int64, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        N.check(self._lib.vs_exchange_collect_dev(self._h, int(B), int(k), _ptr(out_scores), _ptr(out_rows),
+                                                  _stream_ptr(st)))
+        return out_scores, out_rows
+
     def exchange_error(self) -> int:
         return int(self._lib.vs_exchange_error(self._h))
 

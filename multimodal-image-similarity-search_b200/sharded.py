@@ -46,6 +46,16 @@ class PeerExchange:
     def search(self, q, k: int, mode: str = "auto", out_scores=None, out_rows=None):
         return self.index.query_sharded_dev(q, k, out_scores=out_scores, out_rows=out_rows, mode=mode)
 
+    def search_stream(self, queries, k: int, mode: str = "auto", out_scores=None, out_rows=None):
+        """Throughput mode for a stream of independent queries (each ``[b_i, dim]``): every query
+        kernel pushes its candidates into its own slots, ONE collect kernel merges them all."""
+        self.index.exchange_begin()
+        slot = 0
+        for q in queries:
+            self.index.query_push_dev(q, k, slot, mode=mode)
+            slot += 1 if q.dim() == 1 else q.shape[0]
+        return self.index.exchange_collect_dev(slot, k, out_scores=out_scores, out_rows=out_rows)
+
     def exchange_merge(self, s, r, out_scores=None, out_rows=None):
         return self.index.exchange_merge_dev(s, r, out_scores=out_scores, out_rows=out_rows)
 

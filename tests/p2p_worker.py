@@ -51,6 +51,11 @@ def main():
         for b, (s, r) in enumerate(outs):
             ok, why = O.topk_matches(s[0].cpu().numpy(), r[0].cpu().numpy(), full[b], 10, tol)
             assert ok, why
+        # throughput mode: 32 pushes, one collect
+        s, r = p2p.peer_exchange.search_stream([qd[b:b + 1] for b in range(32)], 10, mode="scan")
+        s2, r2 = nccl.search(qd[:32], 10)
+        torch.cuda.synchronize()
+        assert ix.exchange_error() == 0 and torch.equal(r, r2) and torch.equal(s, s2)
         if dtype == "bf16":
             pt = M.ShardedSearcher(p2p.local_topk, p2p.merge, None, p2p.peer_exchange, "tensor")
             s, r = pt.search(qd, 10)

@@ -112,6 +112,34 @@ def test_exchange_kernel_batches_and_tensor_path_one_gpu(gpu):
         ix.close()
 
 
+def test_deferred_push_collect_one_gpu(gpu):
+    """Throughput mode: every query kernel pushes into its own slots, ONE collect kernel per batch."""
+    import torch
+    rng = np.random.default_rng(21)
+    n, d, G = 50_000, 512, 4
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((40, d)).astype(np.float32)
+    idx, streams = _shards(gpu, X, G, "bf16", b_max=64, k_max=32)
+    qd = torch.from_numpy(Q).cuda()
+    for rep in range(3):
+        outs = []
+        for ix, st in zip(idx, streams):
+            with torch.cuda.stream(st):
+                ix.exchange_begin()
+                for b in range(24):                               # 24 single-query scans (fused push)
+                    ix.query_push_dev(qd[b:b + 1], 10, b, mode="scan")
+                ix.query_push_dev(qd[24:40], 10, 24, mode="tensor")   # 16 more through K2 + push kernel
+                outs.append(ix.exchange_collect_dev(40, 10))
+        torch.cuda.synchronize()
+        assert all(ix.exchange_error() == 0 for ix in idx)
+        _check_all([(s[:24], r[:24]) for s, r in outs], Q[:24], X, 10, "bf16")
+        _check_all([(s[24:], r[24:]) for s, r in outs], Q[24:], X, 10, "bf16", round_queries=True)
+    with pytest.raises(gpu.VecSearchError):
+        idx[0].query_push_dev(qd[:8], 10, 60)                     # slots [60,68) exceed B_max=64
+    for ix in idx:
+        ix.close()
+
+
 def test_ragged_and_empty_shards_one_gpu(gpu):
     import torch
     rng = np.random.default_rng(3)
