@@ -12,7 +12,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libvecsearch_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# VS_LIB_PATH: load another build of the same library (profiling experiments only)
+LIB_PATH = os.environ.get("VS_LIB_PATH") or os.path.join(_HERE, LIB_NAME)
 
 VS_F32, VS_BF16 = 0, 1
 VS_Q_AUTO, VS_Q_SCAN, VS_Q_TENSOR = 0, 1, 2
