@@ -36,8 +36,14 @@ constexpr int kCtasPerSm = 2;
 constexpr int kSmemMax = 220 * 1024;
 
 // rows per consumer warp per tile, chosen so a stage (W warps x U rows x pitch) is <= 32 KB
+#ifndef VS_SCAN_TILE_SHIFT
+#define VS_SCAN_TILE_SHIFT 0   // experiments: 1 halves the tile (rows per warp), see profiles/r01_scan_ab.md
+#endif
+__host__ __device__ constexpr int rows_per_tile_target(int cpl) {
+  return (cpl <= 1 ? 64 : cpl <= 2 ? 32 : cpl <= 4 ? 16 : 8) >> VS_SCAN_TILE_SHIFT;
+}
 __host__ __device__ constexpr int rows_per_warp(int cpl, int w) {
-  return (cpl <= 1 ? 64 : cpl <= 2 ? 32 : cpl <= 4 ? 16 : 8) / w > 0 ? (cpl <= 1 ? 64 : cpl <= 2 ? 32 : cpl <= 4 ? 16 : 8) / w : 1;
+  return rows_per_tile_target(cpl) / w > 0 ? rows_per_tile_target(cpl) / w : 1;
 }
 
 struct ScanKernelParams {
@@ -387,7 +393,7 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
     return c >= 1 && c <= 4 ? c : kCtasPerSm;
   }();
   int stages = (smem_budget - fixed) / p.stage_stride;
-  if (stages < 3) stages = (kSmemMax - fixed) / p.stage_stride < 3 ? (kSmemMax - fixed) / p.stage_stride : 3;  // wide rows
+  if (stages < 2) stages = (kSmemMax - fixed) / p.stage_stride < 3 ? (kSmemMax - fixed) / p.stage_stride : 3;  // wide rows
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidValue;
   p.stages = stages;
