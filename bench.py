@@ -145,46 +145,53 @@ def workload_config(args, G):
 # clocks sampling (recipe: /opt/skills/guides/B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region: an NVML polling thread
+    (5 ms period; `nvidia-smi -lms` needs ~100 ms to start, too slow for short multi-GPU runs)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.proc = None
-        self.gpu = gpu_index
+        import threading
+        self.samples, self.err, self._stop = [], None, threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception as e:                        # noqa: BLE001
+            self.err = f"nvml unavailable: {type(e).__name__}"
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                     int(self.reasons_fn(self.h))))
+            except Exception as e:                    # noqa: BLE001
+                self.err = f"nvml sample failed: {type(e).__name__}"
+                return
+            self._stop.wait(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, pw, reasons = [], [], [], set()
-        for ln in out.splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if self.err and not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        mask = 0
+        for _, _, m in self.samples:
+            mask |= m
+        return {"sm_mhz": float(np.median([c for c, _, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                "power_w_max": float(max(p for _, p, _ in self.samples)), "samples": len(self.samples),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit)}
 
 
 # ------------------------------------------------------------------------------------------------
