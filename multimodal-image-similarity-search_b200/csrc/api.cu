@@ -252,7 +252,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
   }
   int path = mode;
   if (path == VS_Q_AUTO)
-    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && vs::tensor_dim_ok(ix->dim) &&
             vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
   if (path == VS_Q_TENSOR) {
     if (ix->dtype != VS_BF16) return fail(VS_ERR_UNSUPPORTED, "tensor path needs bf16 storage");
@@ -668,7 +668,7 @@ int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
     CU(cudaMemset(ix->d_tickets.p, 0, ix->d_tickets.bytes));
     ix->tickets_n = kScanBatch;
   }
-  if (ix->dtype == VS_BF16 && ix->dim % 8 == 0 && ix->dim <= 768 && vs::tensor_path_available()) {
+  if (ix->dtype == VS_BF16 && vs::tensor_dim_ok(ix->dim) && vs::tensor_path_available()) {
     const int64_t rows_hint = ix->cap > ix->n ? ix->cap : ix->n;
     const int kt = k_max < vs::kMaxTensorK ? k_max : vs::kMaxTensorK;
     CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B_max, ix->dim, kt, ix->sm_count, rows_hint > 0 ? rows_hint : 1)));
@@ -773,7 +773,7 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
   if (ix->xc.G == 1) return query_dev_locked(ix, q_dev, B, k, require_bits, mode, out_scores_dev, out_rows_dev, st);
   int path = mode;
   if (path == VS_Q_AUTO)
-    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && vs::tensor_dim_ok(ix->dim) &&
             vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
   // fused form: the shard's result never leaves the scan kernel (one launch, exchange inside)
   if (path == VS_Q_SCAN && ix->n > 0 && B <= kScanBatch && B <= ix->xc.Bmax) {
@@ -821,7 +821,7 @@ int vs_query_topk_push_dev(vs_index_t* ix, const float* q_dev, int B, int k, con
   cudaStream_t st = pick_stream(ix, stream);
   int path = mode;
   if (path == VS_Q_AUTO)
-    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && ix->dim % 8 == 0 && ix->dim <= 768 &&
+    path = (ix->dtype == VS_BF16 && B >= 16 && k <= vs::kMaxTensorK && vs::tensor_dim_ok(ix->dim) &&
             vs::tensor_path_available()) ? VS_Q_TENSOR : VS_Q_SCAN;
   float* xs = (float*)ix->d_xs.p;
   int64_t* xr = (int64_t*)ix->d_xr.p;

@@ -52,6 +52,7 @@ struct TcParams {
   int n_slices;            // corpus slices (top-k / filter); one cluster per slice per pass
   int tiles_per_slice;
   int n_items;             // work items per cluster sequence
+  int a_stream;            // 1: the A block is NOT resident; its k-block travels with every B stage (wide rows)
   int prefetch;            // B stages to prefetch into L2 ahead of the smem ring
   int debug_noepi;         // VS_TC_DEBUG_NOEPI=1: epilogue only hands the accumulator back (profiling aid)
   unsigned long long* dbg; // VS_TC_DEBUG_COUNT=1: [groups, slow-path entries, lanes that hit, inserts]
@@ -232,9 +233,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 128B swizzle: 1024-B aligned
+  // resident A: [A: kb_count blocks][stages x B tile]; streamed A: [stages x (B tile | A k-block)]
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)p.kb_count * kABlockBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * kStageBytes);
+  uint8_t* sB = smem + (p.a_stream ? 0 : (size_t)p.kb_count * kABlockBytes);
+  const uint32_t stage_stride = kStageBytes + (p.a_stream ? kABlockBytes : 0u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * stage_stride);
   uint64_t* empty = full + kTcMaxStages;
   uint64_t* tfull = empty + kTcMaxStages;
   uint64_t* tempty = tfull + 4;
@@ -295,12 +298,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         int ablock;
         uint32_t t0, t1;
         item_range(w, ablock, t0, t1);
-        // A block: resident for the whole item
-        if (n_item > 0) mbar_wait(a_empty, (n_item - 1) & 1);
-        mbar_expect_tx(a_full, (uint32_t)p.kb_count * kABlockBytes);
         const int a_row = MODE == kModeDedup ? (int)(p.a_row_lo + (int64_t)ablock * kTcM) : ablock * kTcM;
-        for (int kb = 0; kb < p.kb_count; ++kb)
-          tma_load_2d(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+        if (!p.a_stream) {
+          // A block: resident for the whole item
+          if (n_item > 0) mbar_wait(a_empty, (n_item - 1) & 1);
+          mbar_expect_tx(a_full, (uint32_t)p.kb_count * kABlockBytes);
+          for (int kb = 0; kb < p.kb_count; ++kb)
+            tma_load_2d(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+        }
         // L2 prefetch runs `prefetch` stages ahead of the smem ring (this CTA's part of each box)
         const uint32_t n_st = (t1 - t0) * (uint32_t)p.kb_count;
         auto prefetch_stage = [&](uint32_t idx) {
@@ -318,8 +323,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const uint32_t use = it / p.stages;
             if (p.prefetch > 0) prefetch_stage(idx + (uint32_t)p.prefetch);
             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);   // all C CTAs have consumed this stage
-            mbar_expect_tx(&full[st], kStageBytes);              // the whole tile: C parts from C CTAs
-            uint8_t* dst = sB + (size_t)st * kStageBytes + (size_t)rank * kPartRows * 128;
+            // the whole B tile (C parts from C CTAs) + this CTA's own A k-block when A is streamed
+            mbar_expect_tx(&full[st], kStageBytes + (p.a_stream ? kABlockBytes : 0u));
+            if (p.a_stream)   // re-read per tile from L2 (the A block is 128 x dim bf16 <= 256 KB, L2 resident)
+              tma_load_2d(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
+            uint8_t* dst = sB + (size_t)st * stage_stride + (size_t)rank * kPartRows * 128;
             const int row = (int)(t * BN + rank * kPartRows);
             if (C > 1)
               tma_load_2d_mc(dst, &tmB, kb * kTcKB, row, &full[st], kMask, pol_stream);
@@ -338,8 +346,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         int ablock;
         uint32_t t0, t1;
         item_range(w, ablock, t0, t1);
-        mbar_wait(a_full, n_item & 1);
-        tc_fence_after();
+        if (!p.a_stream) {
+          mbar_wait(a_full, n_item & 1);
+          tc_fence_after();
+        }
         for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t acc = tile_ctr % ACC;
           const uint32_t use = tile_ctr / ACC;
@@ -350,8 +360,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int st = it % p.stages;
             mbar_wait(&full[st], (it / p.stages) & 1);
             tc_fence_after();
-            const uint64_t da = make_smem_desc(smem_u32(sA + (size_t)kb * kABlockBytes));
-            const uint64_t db = make_smem_desc(smem_u32(sB + (size_t)st * kStageBytes));
+            const uint64_t da = make_smem_desc(smem_u32(p.a_stream ? sB + (size_t)st * stage_stride + kStageBytes
+                                                                   : sA + (size_t)kb * kABlockBytes));
+            const uint64_t db = make_smem_desc(smem_u32(sB + (size_t)st * stage_stride));
 #pragma unroll
             for (int k = 0; k < kTcKB / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance start address by 2 (16-B units)
               umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
           umma_commit(&tfull[acc]);                // accumulator ready for the epilogue
         }
-        umma_commit(a_empty);                      // A block may be overwritten
+        if (!p.a_stream) umma_commit(a_empty);     // A block may be overwritten
       }
     }
     __syncwarp();
@@ -629,7 +640,7 @@ static int tc_max_cluster() {
 }
 
 struct TcPlan {
-  int BN, stages, kb_count, Dp;
+  int BN, stages, kb_count, Dp, a_stream;
   size_t smem;
   bool ok;
 };
@@ -641,7 +652,23 @@ static TcPlan plan_for(int dim) {
   const size_t a_bytes = (size_t)pl.kb_count * kTcM * 128;
   const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/;
   auto stages_for = [&](int bn) { return (int)(((size_t)kTcSmemMax - fixed - a_bytes) / ((size_t)bn * 128)); };
-  pl.ok = a_bytes + fixed + 2 * 128 * 128 <= (size_t)kTcSmemMax;
+  // Resident A needs kb_count x 16 KB of smem.  At dim 768 that left 2 x 16 KB of B stages and the
+  // kernel was TMA-latency bound (dedup 200k x 768: 0.45 PFLOP/s).  Streaming the A k-block with every
+  // stage instead (16 KB more L2->SM traffic per stage, A block stays L2 resident) gives a 4-deep
+  // ring of BN = 256 tiles at ANY dim: dedup 1.10 PFLOP/s, and the 512-d top-k gains 8 % as well
+  // (profiles/r01_tensor_path.md), so it is the default; VS_TC_ASTREAM=0 keeps A resident.
+  static const int force_stream = env_int("VS_TC_ASTREAM", -1);
+  const bool resident_ok = a_bytes + fixed + 2 * 128 * 128 <= (size_t)kTcSmemMax;
+  pl.a_stream = force_stream >= 0 ? (force_stream != 0 || !resident_ok || stages_for(pl.BN) < 2) : 1;
+  if (pl.a_stream) {
+    const size_t stride = (size_t)pl.BN * 128 + (size_t)kTcM * 128;
+    pl.stages = (int)(((size_t)kTcSmemMax - fixed) / stride);
+    if (pl.stages > kTcMaxStages) pl.stages = kTcMaxStages;
+    pl.ok = pl.stages >= 2;
+    pl.smem = fixed + (size_t)pl.stages * stride;
+    return pl;
+  }
+  pl.ok = resident_ok;
   if (pl.ok && stages_for(pl.BN) < 3) pl.BN = 128;
   pl.stages = pl.ok ? stages_for(pl.BN) : 0;
   if (pl.stages > kTcMaxStages) pl.stages = kTcMaxStages;
@@ -781,6 +808,7 @@ static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   p.n_tiles = (uint32_t)((a.n_rows + pl.BN - 1) / pl.BN);
   p.kb_count = pl.kb_count;
   p.stages = pl.stages;
+  p.a_stream = pl.a_stream;
   p.prefetch = tc_prefetch();
   static const int noepi = env_int("VS_TC_DEBUG_NOEPI", 0);
   p.debug_noepi = noepi;
@@ -794,7 +822,8 @@ static void plan_slices(TcParams& p, int n_clusters) {
   p.n_items = p.n_slices;
 }
 
-static bool dims_ok(const TensorArgs& a) { return a.dim >= 8 && a.dim % 8 == 0 && a.ld_elems % 8 == 0; }
+static bool dims_ok(const TensorArgs& a) { return tensor_dim_ok(a.dim) && a.ld_elems % 8 == 0; }
+bool tensor_dim_ok(int dim) { return dim >= 8 && dim % 8 == 0 && dim <= 4096; }
 
 cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k, void* workspace, float* out_s,
                                int64_t* out_r, int sm_count, cudaStream_t st) {

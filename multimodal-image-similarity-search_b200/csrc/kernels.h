@@ -93,5 +93,6 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
                                 int64_t* out_i, int64_t* out_j, float* out_score, unsigned long long* out_count,
                                 void* workspace, int sm_count, cudaStream_t st);
 bool tensor_path_available();
+bool tensor_dim_ok(int dim);   // dim % 8 == 0, dim <= 4096 (A block resident up to 512, streamed beyond)
 
 }  // namespace vs

@@ -31,7 +31,9 @@ def _check_topk(s, r, Q, X, k, valid=None):
 
 @pytest.mark.parametrize("n,d,B,k", [(1000, 512, 16, 10), (70000, 512, 130, 10), (5000, 256, 300, 32),
                                      (3000, 768, 20, 5), (4096, 64, 128, 10), (2500, 200, 17, 10),
-                                     (130, 512, 1024, 10)])
+                                     (130, 512, 1024, 10),
+                                     # dim > 512: the A block is streamed with every stage instead of resident
+                                     (40000, 768, 300, 10), (6000, 1024, 130, 10), (3000, 1536, 40, 32), (2000, 576, 16, 10)])
 def test_tensor_topk_matches_oracle(gpu, n, d, B, k):
     rng = np.random.default_rng(n + d + B)
     X = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)
@@ -93,7 +95,7 @@ def test_tensor_pre_filter_bits(gpu):
 
 
 @pytest.mark.parametrize("n,d,F,tau", [(300, 96, 6, 0.1), (10000, 512, 256, 0.08), (1100, 512, 3, 0.0),
-                                       (5000, 768, 130, 0.05)])
+                                       (5000, 768, 130, 0.05), (3000, 1024, 200, 0.04)])
 def test_filter_sweep_matches_oracle(gpu, n, d, F, tau):
     if (n, d, F) == (300, 96, 6):
         g = np.load(GOLD)
@@ -116,7 +118,7 @@ def test_filter_sweep_matches_oracle(gpu, n, d, F, tau):
     ix.close()
 
 
-@pytest.mark.parametrize("n,d", [(300, 96), (20000, 768), (9000, 512)])
+@pytest.mark.parametrize("n,d", [(300, 96), (20000, 768), (9000, 512), (5000, 1024)])
 def test_dedup_matches_oracle(gpu, n, d):
     if (n, d) == (300, 96):
         g = np.load(GOLD)
