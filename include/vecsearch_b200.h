@@ -93,6 +93,8 @@ int vs_get_mask_bits(const vs_index_t* ix, int64_t row, uint64_t bits[VS_MASK_WO
 
 /* Copy stored rows back as float32 (Collection.get(include=["embeddings"]) and persistence). */
 int vs_get_rows_host(const vs_index_t* ix, int64_t first_row, int64_t n, float* out);
+/* Same into a DEVICE buffer [n, dim] float32 (replicating shards for the all-pairs pass). */
+int vs_get_rows_dev(const vs_index_t* ix, int64_t first_row, int64_t n, float* out_dev, void* stream);
 
 /* ---- query: Collection.query(query_embeddings=[...], n_results=k, ...)
  *      (backend/app/main.py:761-765; legacy app.py:310-314).

@@ -540,6 +540,18 @@ int vs_get_rows_host(const vs_index_t* cix, int64_t first_row, int64_t n, float*
   return VS_OK;
 }
 
+int vs_get_rows_dev(const vs_index_t* cix, int64_t first_row, int64_t n, float* out_dev, void* stream) {
+  vs_index* ix = const_cast<vs_index*>(cix);
+  if (!ix || (!out_dev && n > 0)) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (first_row < 0 || n < 0 || first_row + n > ix->n) return fail(VS_ERR_ARG, "row range out of bounds");
+  if (n == 0) return VS_OK;
+  DeviceGuard g(ix->device);
+  const char* src = (const char*)ix->rows + (size_t)first_row * ix->ld * ix->esize;
+  CU(vs::launch_export(src, n, ix->dim, ix->dtype, ix->ld, out_dev, pick_stream(ix, stream)));
+  return VS_OK;
+}
+
 int vs_query_topk_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits, int mode,
                       float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
   if (!ix) return fail(VS_ERR_ARG, "index is NULL");

@@ -131,6 +131,16 @@ class DeviceIndex:
         N.check(self._lib.vs_get_rows_host(self._h, int(first), int(n), out.ctypes.data))
         return out
 
+    def get_rows_dev(self, first: int, n: int, out=None, stream=None):
+        """Stored rows [first, first+n) as a float32 CUDA tensor [n, dim] (exact for bf16 storage)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        N.check(self._lib.vs_get_rows_dev(self._h, int(first), int(n), _ptr(out), _stream_ptr(st)))
+        return out
+
     # -- query ----------------------------------------------------------------------------
     def query(self, q, k: int, require_bits: Optional[Sequence[int]] = None, mode: str = "auto"
               ) -> Tuple[np.ndarray, np.ndarray]:

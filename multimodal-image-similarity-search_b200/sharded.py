@@ -25,6 +25,66 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+def triangle_bounds(n_rows: int, world_size: int, rank: int, align: int = 128) -> Tuple[int, int]:
+    """Row range ``[lo, hi)`` of rank ``rank`` for the all-pairs pass (pairs i<j): row i owns the
+    ``n-1-i`` pairs to its right, so equal WORK means boundaries at ``n*(1-sqrt(1-r/G))`` (not equal
+    row counts); rounded to ``align`` rows (the kernel's 128-row A blocks)."""
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world_size:
+            return n_rows
+        x = n_rows * (1.0 - (1.0 - r / world_size) ** 0.5)
+        return min(n_rows, int(round(x / align)) * align)
+    return cut(rank), cut(rank + 1)
+
+
+def replicate_index(local_index, n_total: int, group=None, chunk_rows: int = 1 << 16):
+    """All-gather the row shards into a NEW full DeviceIndex on every rank (the all-pairs pass needs
+    every column on every GPU): each rank broadcasts its stored rows in chunks
+    (device to device over NCCL) and every rank appends them in global row order."""
+    import torch
+    import torch.distributed as dist
+    from .index import DeviceIndex
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", local_index.device)
+    full = DeviceIndex(local_index.dim, local_index.dtype, device=local_index.device, capacity=n_total)
+    buf = torch.empty((chunk_rows, local_index.dim), dtype=torch.float32, device=dev)
+    for src in range(world):
+        lo, hi = shard_bounds(n_total, world, src)
+        for c0 in range(lo, hi, chunk_rows):
+            m = min(chunk_rows, hi - c0)
+            view = buf[:m]
+            if rank == src:
+                local_index.get_rows_dev(c0 - lo, m, out=view)
+            dist.broadcast(view, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+            full.add(view)
+    assert len(full) == n_total
+    return full
+
+
+def find_duplicates_sharded(local_dedup: Callable, n_total: int, group=None):
+    """All-pairs duplicate detection split over the ranks: rank r runs
+    ``local_dedup(row_lo, row_hi) -> (i, j, score)`` (numpy, global rows, pairs i<j with i in the
+    range) on its triangle slice (``triangle_bounds``); the pair lists are gathered on every rank and
+    returned sorted by (i, j).  ``local_dedup`` is ``full_index.dedup(tau, lo, hi)`` in production."""
+    import numpy as np
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = triangle_bounds(n_total, world, rank)
+    i, j, s = local_dedup(lo, hi) if hi > lo else (np.empty(0, np.int64), np.empty(0, np.int64), np.empty(0, np.float32))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (np.asarray(i), np.asarray(j), np.asarray(s)), group=group)
+        i = np.concatenate([p[0] for p in parts])
+        j = np.concatenate([p[1] for p in parts])
+        s = np.concatenate([p[2] for p in parts])
+    order = np.lexsort((j, i))
+    return i[order], j[order], s[order]
+
+
 class PeerExchange:
     """Exchange buffers of ``vs_query_topk_sharded_dev`` for one process-per-GPU group: every rank
     allocates its buffer in the library, the CUDA IPC handles are all-gathered once at set-up

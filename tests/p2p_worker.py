@@ -64,6 +64,20 @@ def main():
             for b in range(Q.shape[0]):
                 ok, why = O.topk_matches(s[b].cpu().numpy(), r[b].cpu().numpy(), fullr[b], 10, tol)
                 assert ok, why
+        if dtype == "bf16":
+            # all-pairs pass: replicate the shards, split the triangle, gather the pairs
+            Xd = X[:20_000].copy()
+            Xd[15_000:15_100] = Xd[100:200] + (0.1 / np.sqrt(d)) * rng.standard_normal((100, d)).astype(np.float32)
+            dlo, dhi = M.shard_bounds(len(Xd), world, rank)
+            sh = M.DeviceIndex(d, "bf16", device=local, row_base=dlo)
+            sh.add(Xd[dlo:dhi])
+            full_ix = M.replicate_index(sh, len(Xd))
+            assert np.array_equal(full_ix.get_rows(0, 64), O.bf16_round(Xd[:64]))
+            pi, pj, ps = M.find_duplicates_sharded(lambda lo_, hi_: full_ix.dedup(0.95, lo_, hi_), len(Xd))
+            wi, wj, ws = O.dedup_pairs(Xd, 0.95)
+            assert set(zip(pi.tolist(), pj.tolist())) == set(zip(wi.tolist(), wj.tolist())) and len(wi) >= 100
+            full_ix.close()
+            sh.close()
         got = [torch.zeros_like(r) for _ in range(world)]
         dist.all_gather(got, r)
         assert all(torch.equal(got[0], g) for g in got)

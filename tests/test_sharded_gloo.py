@@ -72,3 +72,52 @@ def test_world_size_2_matches_single_shard():
         p.join(150)
         assert p.exitcode == 0
     assert out.get(timeout=5) == "ok"
+
+
+def test_triangle_bounds_cover_and_balance():
+    from mmiss_b200.sharded import triangle_bounds
+    for n, g in ((2_000_000, 8), (200_000, 4), (1000, 3), (100, 8), (0, 2)):
+        spans = [triangle_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        if n >= 100_000:                       # equal WORK (pairs to the right), not equal rows
+            work = [sum(n - 1 - i for i in (lo, hi - 1)) / 2 * (hi - lo) for lo, hi in spans]
+            assert max(work) / (sum(work) / g) < 1.02
+            assert spans[0][1] - spans[0][0] < spans[-1][1] - spans[-1][0]
+
+
+def _dedup_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmiss_b200.sharded import find_duplicates_sharded
+    rng = np.random.default_rng(5)
+    n, d = 700, 48
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[600:650] = X[10:60] + 0.01 * rng.standard_normal((50, d)).astype(np.float32)
+    wi, wj, ws = O.dedup_pairs(X, 0.95)
+
+    def local(lo, hi):                                  # the oracle restricted to rows [lo, hi)
+        m = (wi >= lo) & (wi < hi)
+        return wi[m], wj[m], ws[m]
+
+    i, j, s = find_duplicates_sharded(local, n)
+    assert np.array_equal(i, wi) and np.array_equal(j, wj) and np.array_equal(s, ws) and len(i) >= 50
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_2_sharded_dedup():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_dedup_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
