@@ -118,6 +118,17 @@ def run_reference(args):
     t0 = time.perf_counter()
     base = cpu_reference_qps(args.rows, args.dim, args.k, budget_s=min(60.0, 4.0 * steps_total))
     wall = time.perf_counter() - t0
+    # the index the reference really queries is chromadb's HNSW (approximate): its recall against the
+    # exact result and its CPU query rate, from the hnswlib restatement in oracle/ on a bounded sample
+    hnsw = None
+    if args.hnsw_rows > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import hnsw_recall
+            hnsw = [hnsw_recall.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=True),
+                    hnsw_recall.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=False)]
+        except Exception as e:                        # noqa: BLE001 -- gcc missing etc.: report, do not fail the arm
+            hnsw = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -126,7 +137,7 @@ def run_reference(args):
         "config": workload_config(args, 1),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": wall,
+        "gpu_launches": 0, "wall_s": wall, "hnsw_recall_vs_exact": hnsw,
         "note": "chromadb/hnswlib are not installable offline; this is the reference's exact CPU path "
                 "(numpy matmul + top-k) as restated in oracle/, all host threads BLAS uses",
     }
@@ -432,6 +443,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="batched tensor-path extra (0 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: candidate exchange fused into the query kernel over NVLink peer memory, or NCCL all-gather")
+    ap.add_argument("--hnsw-rows", type=int, default=20_000,
+                    help="reference arm: rows of the bounded HNSW recall sample (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
