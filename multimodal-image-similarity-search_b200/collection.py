@@ -33,6 +33,23 @@ FILTER_JSON_KEY = "filter_results_json"   # reference: backend/app/main.py:731, 
 MAX_FILTERS = 256
 
 
+def _is_cuda_rows(x) -> bool:
+    """A float32 CUDA torch tensor: taken as is (encoder output never leaves the GPU)."""
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _as_cuda_rows(x, dim: Optional[int]):
+    import torch
+    t = x.detach()
+    if t.dim() == 1:
+        t = t[None]
+    if t.dim() != 2:
+        raise ValueError(f"embeddings must be [n, dim], got shape {tuple(t.shape)}")
+    if dim is not None and t.shape[1] != dim:
+        raise ValueError(f"Embedding dimension {t.shape[1]} does not match collection dimensionality {dim}")
+    return t.to(torch.float32).contiguous()
+
+
 def _as_rows(embeddings, dim: Optional[int]) -> np.ndarray:
     if hasattr(embeddings, "detach"):          # torch tensor
         embeddings = embeddings.detach().cpu().numpy()
@@ -44,6 +61,16 @@ def _as_rows(embeddings, dim: Optional[int]) -> np.ndarray:
     if dim is not None and a.shape[1] != dim:
         raise ValueError(f"Embedding dimension {a.shape[1]} does not match collection dimensionality {dim}")
     return np.ascontiguousarray(a)
+
+
+class _NoRows:
+    """Placeholder for device rows that need no host copy (in-memory collection: nothing is logged)."""
+
+    def __init__(self, dim: int):
+        self.shape = (0, dim)
+
+    def __getitem__(self, j):
+        return None
 
 
 def _yes(answer: Any) -> bool:
@@ -181,7 +208,8 @@ class Collection:
         if isinstance(ids, str):
             ids = [ids]
         ids = list(ids)
-        rows = _as_rows(embeddings, self.dim)
+        # a CUDA tensor (e.g. a batch of CLIP image embeddings) is ingested device-to-device by K6
+        rows = _as_cuda_rows(embeddings, self.dim) if _is_cuda_rows(embeddings) else _as_rows(embeddings, self.dim)
         n = len(ids)
         if rows.shape[0] != n:
             raise ValueError(f"{n} ids but {rows.shape[0]} embeddings")
@@ -208,9 +236,13 @@ class Collection:
                            [documents[i] for i in keep], log=True)
 
     def _add_rows(self, ids, rows, metadatas, documents, log: bool):
-        ix = self._ensure_index(rows.shape[1])
+        ix = self._ensure_index(int(rows.shape[1]))
         first = ix.add(rows)
         assert first == len(self._ids), "host/device row bookkeeping diverged"
+        if log and self._log is not None and not isinstance(rows, np.ndarray):
+            rows = rows.cpu().numpy()                 # the persistence log stores the f32 rows
+        elif not isinstance(rows, np.ndarray):
+            rows = _NoRows(int(rows.shape[1]))
         for j, id_ in enumerate(ids):
             self._row_of[id_] = first + j
             self._ids.append(id_)
@@ -253,6 +285,13 @@ class Collection:
         if n_results <= 0:
             raise ValueError("n_results must be positive")
         with self._lock:
+            if _is_cuda_rows(query_embeddings):       # device-resident queries: no H2D, only the [B,k] result comes back
+                qd = _as_cuda_rows(query_embeddings, self.dim)
+
+                def run_dev(k, require):
+                    s_, r_ = self._index.query_dev(qd, k, require_bits=require, mode=mode)
+                    return s_.cpu().numpy(), r_.cpu().numpy()
+                return self._run_query(int(qd.shape[0]), n_results, list(include), where_filters, filter_mode, run_dev)
             q = _as_rows(query_embeddings, self.dim)
             return self._run_query(q.shape[0], n_results, list(include), where_filters, filter_mode,
                                    lambda k, require: self._index.query(q, k, require_bits=require, mode=mode))

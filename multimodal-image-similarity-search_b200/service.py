@@ -144,3 +144,77 @@ class SearchService:
         self.collection.add(ids=[image_id], embeddings=[np.asarray(embedding).tolist()], metadatas=[metadata],
                             documents=[description])
         return metadata, True
+
+
+class MicroBatcher:
+    """Server-side micro-batching of concurrent single queries: the
+    reference answers one request at a time (`search_similar`, backend/app/main.py:748-805, called
+    inline from the async routes); under load the requests that arrive within ``max_wait_ms`` of each
+    other are stacked into ONE ``collection.query`` so the batched tcgen05 kernel (K2) serves them in
+    a single pass over the corpus.  Each caller gets exactly what its own
+    ``collection.query(query_embeddings=[e], n_results=n, include=...)`` would have returned."""
+
+    def __init__(self, collection, max_batch: int = 64, max_wait_ms: float = 2.0,
+                 include: Sequence[str] = ("metadatas", "distances")):
+        import threading
+        self.collection, self.max_batch, self.max_wait = collection, int(max_batch), max_wait_ms / 1e3
+        self.include = list(include)
+        self._cv = threading.Condition()
+        self._pending: List[Dict[str, Any]] = []
+        self._closed = False
+        self.batches: List[int] = []                      # sizes of the batches run so far (introspection)
+        self._worker = threading.Thread(target=self._run, daemon=True)
+        self._worker.start()
+
+    def query(self, embedding, n_results: int = 10) -> Dict[str, Any]:
+        """Blocking; thread-safe.  Returns the chromadb-shaped dict for this one query."""
+        import threading
+        req = {"e": np.asarray(embedding, dtype=np.float32).reshape(-1), "n": int(n_results),
+               "done": threading.Event(), "out": None, "err": None}
+        with self._cv:
+            if self._closed:
+                raise RuntimeError("MicroBatcher is closed")
+            self._pending.append(req)
+            self._cv.notify_all()
+        req["done"].wait()
+        if req["err"] is not None:
+            raise req["err"]
+        return req["out"]
+
+    def _run(self):
+        import time
+        while True:
+            with self._cv:
+                while not self._pending and not self._closed:
+                    self._cv.wait()
+                if self._closed and not self._pending:
+                    return
+                deadline = time.monotonic() + self.max_wait
+                while len(self._pending) < self.max_batch and not self._closed:
+                    left = deadline - time.monotonic()
+                    if left <= 0:
+                        break
+                    self._cv.wait(left)
+                batch, self._pending = self._pending[:self.max_batch], self._pending[self.max_batch:]
+            try:
+                n_max = max(r["n"] for r in batch)
+                res = self.collection.query(query_embeddings=np.stack([r["e"] for r in batch]), n_results=n_max,
+                                            include=self.include)
+                self.batches.append(len(batch))
+                for b, r in enumerate(batch):
+                    one = dict(res)
+                    for key in ("ids", "distances", "metadatas", "documents", "embeddings"):
+                        if res.get(key) is not None:
+                            one[key] = [res[key][b][:r["n"]]]
+                    r["out"] = one
+            except Exception as e:                        # noqa: BLE001 -- every waiter gets the error
+                for r in batch:
+                    r["err"] = e
+            for r in batch:
+                r["done"].set()
+
+    def close(self):
+        with self._cv:
+            self._closed = True
+            self._cv.notify_all()
+        self._worker.join(timeout=5)

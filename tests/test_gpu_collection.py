@@ -172,3 +172,42 @@ def test_filter_sweep_and_find_duplicates_on_collection(gpu):
     dups = col.find_duplicates(float(g["dedup_tau"]))
     assert {(a, b) for a, b, _ in dups} == {(f"r{i}", f"r{j}") for i, j in zip(g["dedup_i"], g["dedup_j"])}
     col.close()
+
+
+def test_device_resident_add_and_query(gpu, tmp_path):
+    """SURVEY 8(f2/f4): embeddings produced on the GPU (CLIP output) are ingested and queried without
+    a host round trip; results equal the host-list path (main.py:735-740, 761-765), and the
+    persistent collection still logs the rows."""
+    import torch
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((500, 512)).astype(np.float32)
+    Q = rng.standard_normal((20, 512)).astype(np.float32)
+    ids = [f"img_{i:04x}" for i in range(500)]
+    host = gpu.Collection("h", {"hnsw:space": "cosine"}, dtype="bf16")
+    host.add(ids=ids, embeddings=X.tolist(), metadatas=[{"filename": f"{i}.jpg"} for i in range(500)])
+    client = gpu.PersistentClient(path=str(tmp_path), dtype="bf16")
+    dev = client.create_collection("d", metadata={"hnsw:space": "cosine"})
+    dev.add(ids=ids, embeddings=torch.from_numpy(X).cuda(), metadatas=[{"filename": f"{i}.jpg"} for i in range(500)])
+    dev.add(ids=ids[:3], embeddings=torch.from_numpy(X[:3]).cuda())       # existing ids are skipped
+    assert dev.count() == 500
+    a = host.query(query_embeddings=Q.tolist(), n_results=10, include=["metadatas", "distances"])
+    b = dev.query(query_embeddings=torch.from_numpy(Q).cuda(), n_results=10, include=["metadatas", "distances"])
+    assert a["ids"] == b["ids"] and a["metadatas"] == b["metadatas"]
+    np.testing.assert_allclose(np.array(a["distances"]), np.array(b["distances"]), atol=2e-3)
+    mb = gpu.MicroBatcher(dev, max_batch=32, max_wait_ms=100.0)
+    got = [None] * 20
+    ts = [threading.Thread(target=lambda i=i: got.__setitem__(i, mb.query(Q[i], 5))) for i in range(20)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    mb.close()
+    for i in range(20):
+        assert got[i]["ids"][0] == a["ids"][i][:5]
+    dev.close()
+    again = gpu.PersistentClient(path=str(tmp_path), dtype="bf16").get_collection("d")   # rows were logged
+    assert again.count() == 500
+    c = again.query(query_embeddings=Q[:2].tolist(), n_results=10)
+    assert c["ids"] == a["ids"][:2]
+    again.close()
+    host.close()

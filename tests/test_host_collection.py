@@ -286,3 +286,41 @@ def test_filter_sweep_and_duplicates_api():
     assert len(kept["ids"][0]) == n_yes
     dups = col.find_duplicates(float(g["dedup_tau"]))
     assert [(a, b) for a, b, _ in dups] == [(f"r{i}", f"r{j}") for i, j in zip(g["dedup_i"], g["dedup_j"])]
+
+
+def test_micro_batcher_stacks_concurrent_queries():
+    """concurrent single queries are served by ONE batched collection.query; every
+    caller gets what its own query would have returned (main.py:761-765 shape)."""
+    col = _coll()
+    X = _vecs(200, 16, seed=3)
+    col.add(ids=[f"img_{i}" for i in range(200)], embeddings=X, metadatas=[{"filename": f"{i}.jpg"} for i in range(200)])
+    mb = mmiss_b200.MicroBatcher(col, max_batch=16, max_wait_ms=200.0)
+    Q = _vecs(12, 16, seed=4)
+    want = [col.query(query_embeddings=[q.tolist()], n_results=3 + (i % 4), include=["metadatas", "distances"])
+            for i, q in enumerate(Q)]
+    got = [None] * len(Q)
+
+    def worker(i):
+        got[i] = mb.query(Q[i], n_results=3 + (i % 4))
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(Q))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(30)
+    mb.close()
+    for i in range(len(Q)):
+        assert got[i]["ids"] == want[i]["ids"] and len(got[i]["ids"][0]) == 3 + (i % 4)
+        np.testing.assert_allclose(got[i]["distances"][0], want[i]["distances"][0], atol=1e-6)
+        assert got[i]["metadatas"] == want[i]["metadatas"]
+    assert sum(mb.batches) == len(Q) and max(mb.batches) > 1      # requests really were stacked
+
+
+def test_micro_batcher_propagates_errors():
+    col = _coll()
+    col.add(ids=["a"], embeddings=_vecs(1, 16))
+    mb = mmiss_b200.MicroBatcher(col, max_wait_ms=1.0)
+    with pytest.raises(ValueError):
+        mb.query(np.zeros(7, np.float32), 1)          # wrong dimension: the collection's error reaches the caller
+    mb.close()
+    with pytest.raises(RuntimeError):
+        mb.query(np.zeros(16, np.float32), 1)
