@@ -127,6 +127,70 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* holder_smem, uint32_t ncols
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- cta_group::2 (CTA pair = cluster ranks 2p, 2p+1; the even CTA is the leader and issues the MMAs) ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the pair bit of a shared::cluster address -> the leader's copy
+__device__ __forceinline__ void tmem_alloc2(uint32_t* holder_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA loads issued by either CTA of a pair; the transaction bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
+      "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_cg2(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                   uint16_t mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask),
+      "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows per CTA] * B[N/2 rows per CTA]^T: M = 256 across the pair
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// arrive on the same barrier of another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> f32, issued by ONE thread for the CTA
@@ -221,15 +285,23 @@ __device__ __forceinline__ bool tc_mask_ok(const uint64_t* mask, uint32_t row, c
 // ------------------------------------------------------------------------------------------
 // the kernel.  C = cluster size (CTAs sharing one corpus stream, one A block each)
 // ------------------------------------------------------------------------------------------
-template <int MODE, int BN, int KL, int C>
+// CG = 2: the CTAs (2p, 2p+1) of the cluster form tcgen05 CTA PAIRS.  The even CTA issues ONE
+// M = 256 MMA for both A blocks; each CTA keeps only HALF of every B tile (its BN/2 rows) in smem, so
+// per MMA a CTA reads 4 KB of A + 4 KB of B from smem instead of 4 + 8, and receives 16 + 16 KB per
+// stage instead of 16 + 32.  Accumulators stay per CTA (128 lanes x BN columns), so the epilogue is
+// unchanged.  CG = 2 implies streamed A (p.a_stream) and an even cluster size.
+template <int MODE, int BN, int KL, int C, int CG = 1>
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  static_assert(CG == 1 || (C % 2 == 0), "CTA pairs need an even cluster");
   constexpr int ACC = 512 / BN;              // accumulator buffers in TMEM
-  constexpr uint32_t kStageBytes = BN * 128; // BN rows x 64 bf16
+  constexpr uint32_t kStageBytes = BN * 128 / CG; // B rows held per CTA per stage x 64 bf16
   constexpr uint32_t kPartRows = BN / C;     // rows of each B tile this CTA fetches (and multicasts)
   constexpr uint32_t kABlockBytes = kTcM * 128;
-  constexpr uint32_t kIdesc = make_idesc(kTcM, BN);
+  constexpr uint32_t kIdesc = make_idesc(kTcM * CG, BN);
   constexpr uint16_t kMask = (uint16_t)((1u << C) - 1u);
+  constexpr uint16_t kEvenMask = (uint16_t)(0x5555u & kMask);   // pair leaders
+  constexpr uint32_t kHalfC = C >= 2 ? C / 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 128B swizzle: 1024-B aligned
@@ -248,17 +320,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = C > 1 ? cluster_ctarank() : 0u;
+  const bool leader = CG == 1 || (rank & 1u) == 0u;
   const int cluster_id = blockIdx.x / C;
   const int n_clusters = gridDim.x / C;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], C);   // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(&empty[s], C / CG);   // one tcgen05.commit arrival from every MMA issuer of the cluster
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);   // one arrival per epilogue warp
+      mbar_init(&tempty[a], 8 * CG);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -268,7 +341,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2(tmem_holder, 512); else tmem_alloc(tmem_holder, 512);
+  }
   tc_fence_before();
   if (C > 1) cluster_sync_all(); else __syncthreads();   // barriers of every CTA initialised before remote arrivals
   tc_fence_after();
@@ -323,24 +398,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const uint32_t use = it / p.stages;
             if (p.prefetch > 0) prefetch_stage(idx + (uint32_t)p.prefetch);
             if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);   // all C CTAs have consumed this stage
-            // the whole B tile (C parts from C CTAs) + this CTA's own A k-block when A is streamed
-            mbar_expect_tx(&full[st], kStageBytes + (p.a_stream ? kABlockBytes : 0u));
-            if (p.a_stream)   // re-read per tile from L2 (the A block is 128 x dim bf16 <= 256 KB, L2 resident)
-              tma_load_2d(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
-            uint8_t* dst = sB + (size_t)st * stage_stride + (size_t)rank * kPartRows * 128;
             const int row = (int)(t * BN + rank * kPartRows);
-            if (C > 1)
-              tma_load_2d_mc(dst, &tmB, kb * kTcKB, row, &full[st], kMask, pol_stream);
-            else
-              tma_load_2d(dst, &tmB, kb * kTcKB, row, &full[st], pol_stream);
+            if (CG == 2) {
+              // pair mode: the LEADER's barrier counts everything both CTAs of the pair receive for this
+              // stage (2 A k-blocks + 2 half B tiles).  This CTA's part of the B tile belongs to half
+              // h = rank / (C/2) of the tile and goes to every CTA of parity h (leaders hold half 0).
+              if (leader) mbar_expect_tx(&full[st], 2u * (kStageBytes + kABlockBytes));
+              tma_load_2d_cg2(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
+              const uint32_t h = rank / kHalfC;
+              uint8_t* dst = sB + (size_t)st * stage_stride + (size_t)(rank % kHalfC) * kPartRows * 128;
+              tma_load_2d_mc_cg2(dst, &tmB, kb * kTcKB, row, &full[st], (uint16_t)(kEvenMask << h), pol_stream);
+            } else {
+              // the whole B tile (C parts from C CTAs) + this CTA's own A k-block when A is streamed
+              mbar_expect_tx(&full[st], kStageBytes + (p.a_stream ? kABlockBytes : 0u));
+              if (p.a_stream)   // re-read per tile from L2 (the A block is 128 x dim bf16 <= 256 KB, L2 resident)
+                tma_load_2d(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
+              uint8_t* dst = sB + (size_t)st * stage_stride + (size_t)rank * kPartRows * 128;
+              if (C > 1)
+                tma_load_2d_mc(dst, &tmB, kb * kTcKB, row, &full[st], kMask, pol_stream);
+              else
+                tma_load_2d(dst, &tmB, kb * kTcKB, row, &full[st], pol_stream);
+            }
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer ===============================================================
-    if (lane == 0) {
+    // ================= MMA issuer (pair mode: the leader CTA only) ==============================
+    if (lane == 0 && leader) {
       uint32_t it = 0, n_item = 0, tile_ctr = 0;
       for (int w = cluster_id; w < p.n_items; w += n_clusters, ++n_item) {
         int ablock;
@@ -353,7 +439,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t acc = tile_ctr % ACC;
           const uint32_t use = tile_ctr / ACC;
-          if (use > 0) mbar_wait(&tempty[acc], (use - 1) & 1);
+          if (use > 0) {
+            if (CG == 2) mbar_wait_cluster(&tempty[acc], (use - 1) & 1); else mbar_wait(&tempty[acc], (use - 1) & 1);
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
@@ -364,12 +452,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                                                    : sA + (size_t)kb * kABlockBytes));
             const uint64_t db = make_smem_desc(smem_u32(sB + (size_t)st * stage_stride));
 #pragma unroll
-            for (int k = 0; k < kTcKB / 16; ++k)   // UMMA_K = 16 bf16 = 32 B: advance start address by 2 (16-B units)
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+            for (int k = 0; k < kTcKB / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B: advance start address by 2 (16-B units)
+              if (CG == 2) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+            }
             // frees the stage (in every CTA of the cluster) when these MMAs have read it
-            if (C > 1) umma_commit_mc(&empty[st], kMask); else umma_commit(&empty[st]);
+            if (CG == 2) umma_commit_mc_cg2(&empty[st], kMask);
+            else if (C > 1) umma_commit_mc(&empty[st], kMask);
+            else umma_commit(&empty[st]);
           }
-          umma_commit(&tfull[acc]);                // accumulator ready for the epilogue
+          // accumulator ready for the epilogue (pair mode: of both CTAs)
+          if (CG == 2) umma_commit_mc_cg2(&tfull[acc], (uint16_t)(3u << rank)); else umma_commit(&tfull[acc]);
         }
         if (!p.a_stream) umma_commit(a_empty);     // A block may be overwritten
       }
@@ -522,7 +615,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // this warp is done reading the accumulator buffer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(&tempty[acc]);
+        }
         if (MODE == kModeTopK && p.debug_noepi != 4 && top.threshold() > published) {
           published = top.threshold();
           atomicMax(gb_ptr, score_key(published));
@@ -545,7 +641,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (C > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -640,15 +736,16 @@ static int tc_max_cluster() {
 }
 
 struct TcPlan {
-  int BN, stages, kb_count, Dp, a_stream;
+  int BN, stages, kb_count, Dp, a_stream, cg;
   size_t smem;
   bool ok;
 };
-static TcPlan plan_for(int dim) {
+static TcPlan plan_for_cg(int dim, int cg_request) {
   TcPlan pl;
   pl.kb_count = (dim + kTcKB - 1) / kTcKB;
   pl.Dp = pl.kb_count * kTcKB;
   pl.BN = tc_block_n();
+  pl.cg = 1;
   const size_t a_bytes = (size_t)pl.kb_count * kTcM * 128;
   const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/;
   auto stages_for = [&](int bn) { return (int)(((size_t)kTcSmemMax - fixed - a_bytes) / ((size_t)bn * 128)); };
@@ -660,8 +757,14 @@ static TcPlan plan_for(int dim) {
   static const int force_stream = env_int("VS_TC_ASTREAM", -1);
   const bool resident_ok = a_bytes + fixed + 2 * 128 * 128 <= (size_t)kTcSmemMax;
   pl.a_stream = force_stream >= 0 ? (force_stream != 0 || !resident_ok || stages_for(pl.BN) < 2) : 1;
+  // CTA pairs (tcgen05 cta_group::2, VS_TC_CG=2): needs streamed A, BN = 256 and an even cluster.  Opt-in:
+  // measured on B200 (profiles/r01_tensor_path.md) the pair mainloop is 4 % faster with the epilogue
+  // compiled out (1.30 vs 1.25 PFLOP/s) but 6 % slower with it (1.06 vs 1.13), because the leader's next
+  // MMA into an accumulator buffer must wait for the epilogues of BOTH CTAs (the slower of two).
+  static const int want_cg = env_int("VS_TC_CG", 1);
+  if (pl.a_stream && pl.BN == 256 && want_cg == 2 && cg_request != 1) pl.cg = 2;
   if (pl.a_stream) {
-    const size_t stride = (size_t)pl.BN * 128 + (size_t)kTcM * 128;
+    const size_t stride = (size_t)pl.BN * 128 / pl.cg + (size_t)kTcM * 128;
     pl.stages = (int)(((size_t)kTcSmemMax - fixed) / stride);
     if (pl.stages > kTcMaxStages) pl.stages = kTcMaxStages;
     pl.ok = pl.stages >= 2;
@@ -676,6 +779,8 @@ static TcPlan plan_for(int dim) {
   pl.smem = a_bytes + fixed + (size_t)pl.stages * pl.BN * 128;
   return pl;
 }
+
+static TcPlan plan_for(int dim) { return plan_for_cg(dim, 0); }
 
 static int kl_for(int k) { return k <= 10 ? 10 : 32; }
 static int cluster_for(int chunks) {
@@ -725,10 +830,10 @@ static int tc_prefetch() {
   return v < 0 ? 0 : v > 64 ? 64 : v;
 }
 
-template <int MODE, int BN, int KL, int C>
+template <int MODE, int BN, int KL, int C, int CG>
 static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const TcPlan& pl,
                                int n_clusters_wanted, cudaStream_t st) {
-  auto kern = tc_kernel<MODE, BN, KL, C>;
+  auto kern = tc_kernel<MODE, BN, KL, C, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
@@ -750,9 +855,9 @@ static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 }
 
 // how many clusters of size C (with this kernel's smem) can be co-resident
-template <int MODE, int BN, int KL, int C>
+template <int MODE, int BN, int KL, int C, int CG>
 static int max_clusters(const TcPlan& pl, int sm_count) {
-  auto kern = tc_kernel<MODE, BN, KL, C>;
+  auto kern = tc_kernel<MODE, BN, KL, C, CG>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
     cudaGetLastError();
     return sm_count / C;
@@ -777,21 +882,26 @@ static int max_clusters(const TcPlan& pl, int sm_count) {
   return n;
 }
 
-#define VS_TC_DISPATCH_C(FN, MODE, BN, KL, C, ...)            \
-  ((C) == 8   ? FN<MODE, BN, KL, 8>(__VA_ARGS__)              \
-   : (C) == 4 ? FN<MODE, BN, KL, 4>(__VA_ARGS__)              \
-   : (C) == 2 ? FN<MODE, BN, KL, 2>(__VA_ARGS__)              \
-              : FN<MODE, BN, KL, 1>(__VA_ARGS__))
-#define VS_TC_DISPATCH(FN, MODE, BN, KL, C, ...)                                    \
-  ((BN) == 256 ? ((KL) == 10 ? VS_TC_DISPATCH_C(FN, MODE, 256, 10, C, __VA_ARGS__)  \
-                             : VS_TC_DISPATCH_C(FN, MODE, 256, 32, C, __VA_ARGS__)) \
-               : ((KL) == 10 ? VS_TC_DISPATCH_C(FN, MODE, 128, 10, C, __VA_ARGS__)  \
-                             : VS_TC_DISPATCH_C(FN, MODE, 128, 32, C, __VA_ARGS__)))
+// CG = 2 (CTA pairs) exists for BN = 256 and even clusters only; `pl.cg` selects it at run time
+#define VS_TC_DISPATCH_C1(FN, MODE, BN, KL, C, ...)           \
+  ((C) == 8   ? FN<MODE, BN, KL, 8, 1>(__VA_ARGS__)           \
+   : (C) == 4 ? FN<MODE, BN, KL, 4, 1>(__VA_ARGS__)           \
+   : (C) == 2 ? FN<MODE, BN, KL, 2, 1>(__VA_ARGS__)           \
+              : FN<MODE, BN, KL, 1, 1>(__VA_ARGS__))
+#define VS_TC_DISPATCH_C2(FN, MODE, KL, C, ...)               \
+  ((C) == 8   ? FN<MODE, 256, KL, 8, 2>(__VA_ARGS__)          \
+   : (C) == 4 ? FN<MODE, 256, KL, 4, 2>(__VA_ARGS__)          \
+              : FN<MODE, 256, KL, 2, 2>(__VA_ARGS__))
+#define VS_TC_DISPATCH_KL(FN, MODE, BN, KL, C, CG, ...)                                            \
+  ((BN) == 256 ? (((CG) == 2 && (C) >= 2) ? VS_TC_DISPATCH_C2(FN, MODE, KL, C, __VA_ARGS__)        \
+                                          : VS_TC_DISPATCH_C1(FN, MODE, 256, KL, C, __VA_ARGS__))  \
+               : VS_TC_DISPATCH_C1(FN, MODE, 128, KL, C, __VA_ARGS__))
+#define VS_TC_DISPATCH(FN, MODE, BN, KL, C, CG, ...)                                   \
+  ((KL) == 10 ? VS_TC_DISPATCH_KL(FN, MODE, BN, 10, C, CG, __VA_ARGS__)                \
+              : VS_TC_DISPATCH_KL(FN, MODE, BN, 32, C, CG, __VA_ARGS__))
 
 // filter / dedup epilogues keep no list: only the KL = 10 instantiation exists for them
-#define VS_TC_DISPATCH10(FN, MODE, BN, C, ...)                               \
-  ((BN) == 256 ? VS_TC_DISPATCH_C(FN, MODE, 256, 10, C, __VA_ARGS__)         \
-               : VS_TC_DISPATCH_C(FN, MODE, 128, 10, C, __VA_ARGS__))
+#define VS_TC_DISPATCH10(FN, MODE, BN, C, CG, ...) VS_TC_DISPATCH_KL(FN, MODE, BN, 10, C, CG, __VA_ARGS__)
 
 static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   memset(&p, 0, sizeof(p));
@@ -842,11 +952,13 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
   const int chunks_total = Bp / kTcM;
   for (int c0 = 0; c0 < chunks_total;) {
     const int C = cluster_for(chunks_total - c0);
+    const int cg = C >= 2 ? pl.cg : 1;
+    const TcPlan plc = plan_for_cg(a.dim, cg);
     TcParams p;
-    fill_common(p, a, pl);
+    fill_common(p, a, plc);
     p.gmin = ws.gmin;
     p.gbound = ws.gbound + (size_t)c0 * kTcM;
-    const int ncl = VS_TC_DISPATCH(max_clusters, kModeTopK, pl.BN, KL, C, pl, sm_count);
+    const int ncl = VS_TC_DISPATCH(max_clusters, kModeTopK, plc.BN, KL, C, cg, plc, sm_count);
     plan_slices(p, ncl);
     p.Bp = C * kTcM;
     p.part_s = part_s;
@@ -854,7 +966,7 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
+    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
     if (e != cudaSuccess) return e;
     static const int dbg_count = env_int("VS_TC_DEBUG_COUNT", 0);
     unsigned long long* dbg = nullptr;
@@ -863,7 +975,7 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
       cudaMemsetAsync(dbg, 0, 4 * sizeof(unsigned long long), st);
       p.dbg = dbg;
     }
-    e = VS_TC_DISPATCH(launch_tc_c, kModeTopK, pl.BN, KL, C, tmA, tmB, p, pl, p.n_slices, st);
+    e = VS_TC_DISPATCH(launch_tc_c, kModeTopK, plc.BN, KL, C, cg, tmA, tmB, p, plc, p.n_slices, st);
     if (e != cudaSuccess) return e;
     if (dbg) {
       unsigned long long h[4];
@@ -894,9 +1006,11 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
   const int chunks_total = Bp / kTcM;
   for (int c0 = 0; c0 < chunks_total;) {
     const int C = cluster_for(chunks_total - c0);
+    const int cg = C >= 2 ? pl.cg : 1;
+    const TcPlan plc = plan_for_cg(a.dim, cg);
     TcParams p;
-    fill_common(p, a, pl);
-    const int ncl = VS_TC_DISPATCH10(max_clusters, kModeFilter, pl.BN, C, pl, sm_count);
+    fill_common(p, a, plc);
+    const int ncl = VS_TC_DISPATCH10(max_clusters, kModeFilter, plc.BN, C, cg, plc, sm_count);
     plan_slices(p, ncl);
     p.out_bits = out_bits + (size_t)c0 * kTcM * words_per_filter;
     p.words_per_filter = words_per_filter;
@@ -905,9 +1019,9 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
     CUtensorMap tmA, tmB;
     cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
-    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
+    e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
     if (e != cudaSuccess) return e;
-    e = VS_TC_DISPATCH10(launch_tc_c, kModeFilter, pl.BN, C, tmA, tmB, p, pl, p.n_slices, st);
+    e = VS_TC_DISPATCH10(launch_tc_c, kModeFilter, plc.BN, C, cg, tmA, tmB, p, plc, p.n_slices, st);
     if (e != cudaSuccess) return e;
     c0 += C;
   }
@@ -921,15 +1035,18 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
   if (!pl.ok || !dims_ok(a)) return cudaErrorNotSupported;
   const TcWorkspace ws = carve_workspace(workspace, kTcM, a.dim, 1, sm_count, a.n_rows);
   launch_gmin(a, ws, st);
-  TcParams p;
-  fill_common(p, a, pl);
-  p.gmin = ws.gmin;
-  p.a_row_min = row_lo;
+  const int64_t a_row_min = row_lo;
   row_lo = row_lo / kTcM * kTcM;   // A blocks are 128-row aligned; rows below the caller's row_lo are filtered out
-  p.a_row_lo = row_lo;
-  p.a_row_hi = row_hi;
   const int n_blocks = (int)((row_hi - row_lo + kTcM - 1) / kTcM);
   const int C = cluster_for(n_blocks);
+  const int cg = C >= 2 ? pl.cg : 1;
+  const TcPlan plc = plan_for_cg(a.dim, cg);
+  TcParams p;
+  fill_common(p, a, plc);
+  p.gmin = ws.gmin;
+  p.a_row_min = a_row_min;
+  p.a_row_lo = row_lo;
+  p.a_row_hi = row_hi;
   p.n_items = (n_blocks + C - 1) / C;
   p.tau = tau;
   p.cap = cap;
@@ -940,11 +1057,11 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
   CUtensorMap tmA, tmB;
   cudaError_t e = make_map(&tmA, a.rows, a.n_rows, a.dim, a.ld_elems, kTcM);
   if (e != cudaSuccess) return e;
-  e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, pl.BN / C);
+  e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
   if (e != cudaSuccess) return e;
-  int ncl = VS_TC_DISPATCH10(max_clusters, kModeDedup, pl.BN, C, pl, sm_count);
+  int ncl = VS_TC_DISPATCH10(max_clusters, kModeDedup, plc.BN, C, cg, plc, sm_count);
   if (ncl > p.n_items) ncl = p.n_items;
-  return VS_TC_DISPATCH10(launch_tc_c, kModeDedup, pl.BN, C, tmA, tmB, p, pl, ncl, st);
+  return VS_TC_DISPATCH10(launch_tc_c, kModeDedup, plc.BN, C, cg, tmA, tmB, p, plc, ncl, st);
 }
 
 }  // namespace vs
