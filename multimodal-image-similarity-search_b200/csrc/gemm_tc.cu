@@ -35,6 +35,8 @@ constexpr int kTcM = 128;          // A rows per block (UMMA M)
 constexpr int kTcKB = 64;          // k elements per stage (= 128 B = one swizzle span)
 constexpr int kTcThreads = 320;      // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTcMaxStages = 8;
+constexpr int kInvRing = 4;          // tiles of inverse norms staged ahead of the epilogue
+constexpr int kTcBarrierBytes = 512; // mbarriers + TMEM address holder
 constexpr int kTcSmemMax = 232448; // 227 KB
 
 enum { kModeTopK = 0, kModeFilter = 1, kModeDedup = 2 };
@@ -315,7 +317,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint64_t* tempty = tfull + 4;
   uint64_t* a_full = tempty + 4;
   uint64_t* a_empty = a_full + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_empty + 1);
+  uint64_t* ifull = a_empty + 1;             // inverse norms of a tile staged in smem: ring of kInvRing tiles
+  uint64_t* iempty = ifull + kInvRing;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(iempty + kInvRing);
+  float* s_invt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kTcBarrierBytes);   // [kInvRing][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -335,6 +340,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
+    for (int i = 0; i < kInvRing; ++i) {
+      mbar_init(&ifull[i], 1);
+      mbar_init(&iempty[i], 8);   // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       const uint64_t pol_stream = policy_evict_first();
       const uint64_t pol_keep = policy_evict_last();
-      uint32_t it = 0, n_item = 0;
+      uint32_t it = 0, n_item = 0, ptile = 0;
       for (int w = cluster_id; w < p.n_items; w += n_clusters, ++n_item) {
         int ablock;
         uint32_t t0, t1;
@@ -392,7 +401,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         };
         for (uint32_t i = 0; i < (uint32_t)p.prefetch; ++i) prefetch_stage(i);
         uint32_t idx = 0;
-        for (uint32_t t = t0; t < t1; ++t) {
+        for (uint32_t t = t0; t < t1; ++t, ++ptile) {
+          {
+            // this tile's BN inverse norms -> smem (the epilogue's exact path reads them with LDS instead
+            // of stalling on L2); the array is padded past n_rows, so a whole tile is always in bounds
+            const uint32_t ib = ptile % kInvRing;
+            if (ptile >= (uint32_t)kInvRing) mbar_wait(&iempty[ib], (ptile / kInvRing - 1) & 1);
+            mbar_expect_tx(&ifull[ib], BN * 4);
+            bulk_g2s(s_invt + ib * BN, p.inv_norm + (size_t)t * BN, BN * 4, &ifull[ib], pol_keep);
+          }
           for (int kb = 0; kb < p.kb_count; ++kb, ++it, ++idx) {
             const int st = it % p.stages;
             const uint32_t use = it / p.stages;
@@ -502,6 +519,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (MODE == kModeTopK && p.debug_noepi != 4) gb = key_score(*reinterpret_cast<volatile uint32_t*>(gb_ptr));
         mbar_wait(&tfull[acc], (tile_ctr / ACC) & 1);
         tc_fence_after();
+        const uint32_t ib = tile_ctr % kInvRing;
+        mbar_wait(&ifull[ib], (tile_ctr / kInvRing) & 1);
         const uint32_t row0 = t * BN;
         const int n_groups = p.debug_noepi == 1 ? 0 : BN / 32;   // debug_noepi: profiling aid (see TcParams)
 #pragma unroll 1
@@ -510,12 +529,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
           const uint32_t rg = row0 + g * 32;
           const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
-          const float4* ip = reinterpret_cast<const float4*>(p.inv_norm + rg);   // padded past n_rows
+          const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * BN + g * 32);   // staged by the producer
           if (MODE == kModeFilter) {
             float inv[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 f = __ldg(ip + j);
+              const float4 f = ip[j];
               inv[4 * j] = f.x;
               inv[4 * j + 1] = f.y;
               inv[4 * j + 2] = f.z;
@@ -559,7 +578,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               uint32_t cm = 0;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 f = __ldg(ip + j4);
+                const float4 f = ip[j4];
                 sc[4 * j4] = __uint_as_float(v[4 * j4]) * f.x;
                 sc[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
                 sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
@@ -618,6 +637,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (lane == 0) {
           if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
           else mbar_arrive(&tempty[acc]);
+          mbar_arrive(&iempty[ib]);
         }
         if (MODE == kModeTopK && p.debug_noepi != 4 && top.threshold() > published) {
           published = top.threshold();
@@ -747,7 +767,7 @@ static TcPlan plan_for_cg(int dim, int cg_request) {
   pl.BN = tc_block_n();
   pl.cg = 1;
   const size_t a_bytes = (size_t)pl.kb_count * kTcM * 128;
-  const size_t fixed = 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const size_t fixed = 1024 /*alignment slack*/ + kTcBarrierBytes + (size_t)kInvRing * 256 * 4 /*inverse-norm ring*/;
   auto stages_for = [&](int bn) { return (int)(((size_t)kTcSmemMax - fixed - a_bytes) / ((size_t)bn * 128)); };
   // Resident A needs kb_count x 16 KB of smem.  At dim 768 that left 2 x 16 KB of B stages and the
   // kernel was TMA-latency bound (dedup 200k x 768: 0.45 PFLOP/s).  Streaming the A k-block with every
