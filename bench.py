@@ -44,14 +44,14 @@ HBM_FALLBACK_GBS = 6650.0
 
 def ncu_traffic_bytes(rows_local: int, dim: int, dtype: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per scan launch from the committed `ncu --set full`
-    capture (profiles/r01b_ncu_scan_topk.txt, first launch; taken on 10M x 512 bf16); None for any other shape."""
+    capture (profiles/r01c_ncu_scan_topk.txt, first launch; taken on 10M x 512 bf16); None for any other shape."""
     if (rows_local, dim, dtype) != (10_000_000, 512, "bf16"):
         return None
     try:
         total = 0.0
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         seen = set()
-        for ln in open(os.path.join(ROOT, "profiles", "r01b_ncu_scan_topk.txt")):
+        for ln in open(os.path.join(ROOT, "profiles", "r01c_ncu_scan_topk.txt")):
             key = ln.split("=")[0].strip()
             if key in ("dram__bytes_read.sum", "dram__bytes_write.sum") and key not in seen:
                 seen.add(key)
