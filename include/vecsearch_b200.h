@@ -83,6 +83,10 @@ int vs_add_dev(vs_index_t* ix, const float* rows_dev, int64_t n, int64_t* first_
  *      moved (== old count-1), or -1 if `row` was the last row. */
 int vs_remove(vs_index_t* ix, int64_t row, int64_t* moved_from);
 
+/* Overwrite the vector of an existing row in place (the row-striped sharded collection moves the
+ * LAST global row into a deleted row's slot, which may live on another shard). */
+int vs_set_row_host(vs_index_t* ix, int64_t row, const float* vec);
+
 /* Drop all rows, keep the allocation  (reset path, backend/app/main.py:1058-1098). */
 int vs_clear(vs_index_t* ix);
 

@@ -38,6 +38,7 @@ SYMBOLS = {
     "vs_add_host": (_i, [_p, _p, _i64, C.POINTER(_i64)]),
     "vs_add_dev": (_i, [_p, _p, _i64, C.POINTER(_i64), _p]),
     "vs_remove": (_i, [_p, _i64, C.POINTER(_i64)]),
+    "vs_set_row_host": (_i, [_p, _i64, _p]),
     "vs_clear": (_i, [_p]),
     "vs_set_mask_bits": (_i, [_p, _i64, _p]),
     "vs_get_mask_bits": (_i, [_p, _i64, _p]),

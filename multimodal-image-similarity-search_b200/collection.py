@@ -82,7 +82,7 @@ class Collection:
     """Duck-type of ``chromadb.api.models.Collection`` restricted to what the reference calls."""
 
     def __init__(self, name: str, metadata: Optional[Dict[str, Any]] = None, *, device: int = 0,
-                 dtype: str = "f32", path: Optional[str] = None, row_base: int = 0):
+                 dtype: str = "f32", path: Optional[str] = None, row_base: int = 0, index=None):
         metadata = dict(metadata or {})
         space = metadata.get("hnsw:space", "cosine")
         if space != "cosine":
@@ -90,7 +90,8 @@ class Collection:
         self.name = name
         self.metadata = metadata
         self._device, self._dtype, self._row_base = device, dtype, row_base
-        self._index: Optional[DeviceIndex] = None     # created on first add (dimension fixed then)
+        # created on first add (dimension fixed then), or injected: a ShardedIndex spanning several GPUs
+        self._index: Optional[DeviceIndex] = index
         self._ids: List[str] = []
         self._row_of: Dict[str, int] = {}
         self._metas: List[Optional[Dict[str, Any]]] = []

@@ -490,6 +490,19 @@ int vs_remove(vs_index_t* ix, int64_t row, int64_t* moved_from) {
   return VS_OK;
 }
 
+int vs_set_row_host(vs_index_t* ix, int64_t row, const float* vec) {
+  if (!ix || !vec) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (row < 0 || row >= ix->n) return fail(VS_ERR_ARG, "row %lld out of range [0,%lld)", (long long)row, (long long)ix->n);
+  DeviceGuard g(ix->device);
+  CU(ix->d_stage.reserve((size_t)ix->dim * 4));
+  CU(cudaMemcpyAsync(ix->d_stage.p, vec, (size_t)ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+  char* dst = (char*)ix->rows + (size_t)row * ix->ld * ix->esize;
+  CU(vs::launch_ingest((const float*)ix->d_stage.p, 1, ix->dim, ix->dtype, dst, ix->ld, ix->inv + row, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
 int vs_clear(vs_index_t* ix) {
   if (!ix) return fail(VS_ERR_ARG, "index is NULL");
   std::lock_guard<std::mutex> lk(ix->mu);

@@ -115,6 +115,13 @@ class DeviceIndex:
         N.check(self._lib.vs_remove(self._h, int(row), C.byref(moved)))
         return int(moved.value)
 
+    def set_row(self, row: int, vec):
+        """Overwrite the vector of an existing row in place."""
+        a = np.ascontiguousarray(vec, dtype=np.float32).reshape(-1)
+        if a.shape[0] != self.dim:
+            raise ValueError(f"expected a [{self.dim}] vector")
+        N.check(self._lib.vs_set_row_host(self._h, int(row), a.ctypes.data))
+
     def clear(self):
         N.check(self._lib.vs_clear(self._h))
 

@@ -103,8 +103,9 @@ class PeerExchange:
         index.exchange_attach(ipc_handles=handles)
         dist.barrier(group=group)                                # every rank has mapped every buffer
 
-    def search(self, q, k: int, mode: str = "auto", out_scores=None, out_rows=None):
-        return self.index.query_sharded_dev(q, k, out_scores=out_scores, out_rows=out_rows, mode=mode)
+    def search(self, q, k: int, mode: str = "auto", out_scores=None, out_rows=None, require_bits=None):
+        return self.index.query_sharded_dev(q, k, out_scores=out_scores, out_rows=out_rows, mode=mode,
+                                            require_bits=require_bits)
 
     def search_stream(self, queries, k: int, mode: str = "auto", out_scores=None, out_rows=None):
         """Throughput mode for a stream of independent queries (each ``[b_i, dim]``): every query
@@ -149,14 +150,15 @@ class ShardedSearcher:
             px = PeerExchange(index, group, b_max, k_max)
         elif exchange not in ("nccl", "p2p"):
             raise ValueError("exchange must be 'nccl' or 'p2p'")
-        return cls(lambda q, k: index.query_dev(q, k, mode=mode),
+        return cls(lambda q, k, bits=None: index.query_dev(q, k, mode=mode, require_bits=bits),
                    lambda cs, cr: index.merge_dev(cs, cr), group, px, mode)
 
-    def search(self, q, k: int):
+    def search(self, q, k: int, require_bits=None):
+        """``require_bits``: filter-bit indices every returned row must carry ("pre" filter mode)."""
         import torch
         if self.peer_exchange is not None and self.world_size > 1 and k <= self.peer_exchange.k_max:
-            return self.peer_exchange.search(q, k, self.mode)    # scan/tcgen05 kernel + fused exchange
-        s, r = self.local_topk(q, k)
+            return self.peer_exchange.search(q, k, self.mode, require_bits=require_bits)   # kernel + fused exchange
+        s, r = self.local_topk(q, k) if require_bits is None else self.local_topk(q, k, require_bits)
         if self.world_size == 1:
             return s, r
         B = s.shape[0]

@@ -33,6 +33,13 @@ class FakeIndex:
         self.bits.pop()
         return moved
 
+    def set_row(self, row, vec):
+        self.X[row] = np.asarray(vec, np.float32).reshape(-1)
+
+    def clear(self):
+        self.X = self.X[:0]
+        self.bits = []
+
     def set_filter_bits(self, row, bits):
         self.bits[row] = set(bits)
 

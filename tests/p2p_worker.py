@@ -13,6 +13,10 @@ import mmiss_b200 as M  # noqa: E402
 from oracle import cosine_oracle as O  # noqa: E402
 
 
+def ix_err(sh):
+    return sh.local.exchange_error()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -83,6 +87,40 @@ def main():
         assert all(torch.equal(got[0], g) for g in got)
         dist.barrier()
         ix.close()
+    # ---- the reference's single server process on rank 0, shards served by the other ranks ----------
+    sh = M.ShardedIndex(d, "bf16", device=local, exchange="p2p", mode="scan", b_max=64, k_max=128)
+    if rank != 0:
+        sh.serve()
+    else:
+        n2 = 30_001
+        ids = [f"img_{i:05x}" for i in range(n2)]
+        metas = [{"filename": f"{i}.jpg", "filter_results_json": '{"is it red?": "%s"}' % ("yes" if i % 4 == 0 else "no")}
+                 for i in range(n2)]
+        many = M.Collection("many", {"hnsw:space": "cosine"}, index=sh)
+        one = M.Collection("one", {"hnsw:space": "cosine"}, dtype="bf16", device=local)
+        for col in (one, many):
+            col.add(ids=ids[:20_000], embeddings=X[:20_000], metadatas=metas[:20_000])
+            col.add(ids=ids[20_000:], embeddings=X[20_000:n2], metadatas=metas[20_000:])
+        assert many.count() == n2 and len(sh) == n2
+
+        def same(**kw):
+            a = one.query(query_embeddings=Q[:6].tolist(), **kw)
+            b = many.query(query_embeddings=Q[:6].tolist(), **kw)
+            assert a["ids"] == b["ids"], kw
+            for da, db in zip(a["distances"], b["distances"]):
+                np.testing.assert_allclose(da, db, atol=1e-6)
+        same(n_results=10, include=["metadatas", "distances"])
+        same(n_results=10, include=["distances"], where_filters=["is it red?"], filter_mode="pre")
+        same(n_results=1000, include=["distances"])                          # k > k_max: all-gather + merge path
+        for col in (one, many):
+            col.delete(ids=[ids[3], ids[n2 - 1], ids[12_345]])
+            col.update(ids=[ids[4]], metadatas=[{"filter_results_json": '{"is it red?": "no"}'}])
+        same(n_results=10, include=["metadatas", "distances"])
+        same(n_results=10, include=["distances"], where_filters=["is it red?"], filter_mode="pre")
+        assert ix_err(sh) == 0
+        many.close()
+        one.close()
+    dist.barrier()
     if rank == 0:
         print("p2p worker ok")
     dist.destroy_process_group()

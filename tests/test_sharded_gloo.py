@@ -121,3 +121,87 @@ def test_world_size_2_sharded_dedup():
         p.join(150)
         assert p.exitcode == 0
     assert out.get(timeout=5) == "ok"
+
+
+def _service_worker(rank, world, port, out):
+    """rank 0 = the reference's single server process with an ordinary Collection on a
+    ShardedIndex; the other ranks serve.  Every Collection operation the reference uses must give the
+    same answers as a single-shard Collection (backend/app/main.py:735-740, 761-765, 503-510, 1069)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmiss_b200 import collection as C
+    from mmiss_b200.sharded_index import ShardedIndex
+    from tests.fake_index import FakeIndex
+
+    def searcher_factory(ix):
+        def local_topk(q, kk, bits=None):
+            s, r = ix.query(q.numpy(), kk, require_bits=bits)
+            return torch.from_numpy(s), torch.from_numpy(r)
+
+        def merge(cs, cr):
+            s, r = O.merge_topk(cs.numpy(), cr.numpy(), cs.shape[2])
+            return torch.from_numpy(s), torch.from_numpy(r)
+        return ShardedSearcher(local_topk, merge)
+
+    sh = ShardedIndex(24, "f32", index_factory=FakeIndex, searcher_factory=searcher_factory)
+    if rank != 0:
+        sh.serve()
+        dist.destroy_process_group()
+        return
+    C.DeviceIndex = FakeIndex
+    one = C.Collection("one", {"hnsw:space": "cosine"})
+    many = C.Collection("many", {"hnsw:space": "cosine"}, index=sh)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((61, 24)).astype(np.float32)
+    ids = [f"img_{i:02d}" for i in range(61)]
+    metas = [{"filename": f"{i}.jpg", "filter_results_json": '{"is it red?": "%s"}' % ("yes" if i % 3 == 0 else "no")}
+             for i in range(61)]
+    for col in (one, many):
+        col.add(ids=ids[:40], embeddings=X[:40].tolist(), metadatas=metas[:40])
+        col.add(ids=ids[40:], embeddings=X[40:], metadatas=metas[40:])        # second batch: striping continues
+        col.add(ids=ids[:2], embeddings=X[:2])                                 # existing ids are skipped
+    assert many.count() == one.count() == 61 and len(sh) == 61
+    Q = rng.standard_normal((5, 24)).astype(np.float32)
+
+    def same(**kw):
+        a, b = one.query(query_embeddings=Q.tolist(), **kw), many.query(query_embeddings=Q.tolist(), **kw)
+        assert a["ids"] == b["ids"], (kw, a["ids"], b["ids"])
+        for da, db in zip(a["distances"], b["distances"]):                      # ragged after a post-filter
+            np.testing.assert_allclose(da, db, atol=1e-6)
+        assert a["metadatas"] == b["metadatas"]
+    same(n_results=10, include=["metadatas", "distances"])
+    same(n_results=100, include=["metadatas", "distances"])                    # clamped to count()
+    same(n_results=7, include=["metadatas", "distances"], where_filters=["is it red?"], filter_mode="post")
+    same(n_results=7, include=["metadatas", "distances"], where_filters=["is it red?"], filter_mode="pre")
+    for col in (one, many):                                                    # delete: last row moves across shards
+        col.delete(ids=[ids[5], ids[60], ids[17]])
+        col.update(ids=[ids[6]], metadatas=[{"filter_results_json": '{"is it red?": "no"}'}])
+    assert many.count() == 58
+    same(n_results=10, include=["metadatas", "distances"])
+    same(n_results=9, include=["metadatas", "distances"], where_filters=["is it red?"], filter_mode="pre")
+    a = one.get(ids=[ids[30]], include=["embeddings", "metadatas"])
+    b = many.get(ids=[ids[30]], include=["embeddings", "metadatas"])
+    assert a["ids"] == b["ids"] and a["metadatas"] == b["metadatas"]
+    np.testing.assert_allclose(a["embeddings"][0], b["embeddings"][0])
+    mm = many.query_multimodal(Q[:2], Q[2:4], 0.3, n_results=4)
+    mo = one.query_multimodal(Q[:2], Q[2:4], 0.3, n_results=4)
+    assert mm["ids"] == mo["ids"]
+    many.close()                                                               # releases the workers
+    out.put("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_3_sharded_collection_service():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_service_worker, args=(r, 3, port, out)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
