@@ -70,6 +70,9 @@ int vs_dtype(const vs_index_t* ix);
 
 /* Offset added to every row number this shard reports (global row = row_base + local row). */
 int vs_set_row_base(vs_index_t* ix, int64_t row_base);
+/* General form: reported row = row_base + local row * row_stride.  Row-STRIPED shards (global row g
+ * on shard g % G) use (shard, G), so every kernel reports and tie-breaks on true global rows. */
+int vs_set_row_map(vs_index_t* ix, int64_t row_base, int64_t row_stride);
 
 /* ---- ingest: Collection.add(ids, embeddings, ...)  (backend/app/main.py:735-740).
  *      Appends n float32 rows [n, dim] (row-major, contiguous); the kernel casts to the storage

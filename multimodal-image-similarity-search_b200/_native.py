@@ -35,6 +35,7 @@ SYMBOLS = {
     "vs_dim": (_i, [_p]),
     "vs_dtype": (_i, [_p]),
     "vs_set_row_base": (_i, [_p, _i64]),
+    "vs_set_row_map": (_i, [_p, _i64, _i64]),
     "vs_add_host": (_i, [_p, _p, _i64, C.POINTER(_i64)]),
     "vs_add_dev": (_i, [_p, _p, _i64, C.POINTER(_i64), _p]),
     "vs_remove": (_i, [_p, _i64, C.POINTER(_i64)]),

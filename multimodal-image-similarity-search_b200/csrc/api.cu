@@ -83,6 +83,7 @@ struct vs_index {
   int64_t n = 0;
   int64_t cap = 0;
   int64_t row_base = 0;
+  int64_t row_stride = 1;
   int sm_count = 148;
   int last_path = 0;
   void* rows = nullptr;
@@ -267,6 +268,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     ta.ld_elems = ix->ld;
     ta.n_rows = ix->n;
     ta.row_base = ix->row_base;
+    ta.row_stride = ix->row_stride;
     CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(B, ix->dim, k, ix->sm_count, ix->n)));
     CU(vs::launch_tensor_topk(ta, q_dev, B, k, ix->d_tensor.p, out_s, out_r, ix->sm_count, st));
     ix->last_path = VS_Q_TENSOR;
@@ -305,6 +307,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     a.ld_bytes = ld_bytes;
     a.n_rows = ix->n;
     a.row_base = ix->row_base;
+    a.row_stride = ix->row_stride;
     a.part_s = (float*)ix->d_part_s.p;
     a.part_r = (uint32_t*)ix->d_part_r.p;
     a.tickets = (unsigned int*)ix->d_tickets.p;
@@ -318,7 +321,7 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
     }
     CU(vs::launch_scan(a, ix->sm_count, st));
     if (large_k)
-      CU(vs::launch_select((const float*)ix->d_scores.p, ix->n, nb, k, ix->row_base, ix->d_select.p, a.out_s, a.out_r, st));
+      CU(vs::launch_select((const float*)ix->d_scores.p, ix->n, nb, k, ix->row_base, ix->row_stride, ix->d_select.p, a.out_s, a.out_r, st));
   }
   ix->last_path = VS_Q_SCAN;
   return VS_OK;
@@ -411,6 +414,15 @@ int vs_set_row_base(vs_index_t* ix, int64_t row_base) {
   if (!ix) return fail(VS_ERR_ARG, "index is NULL");
   std::lock_guard<std::mutex> lk(ix->mu);
   ix->row_base = row_base;
+  return VS_OK;
+}
+
+int vs_set_row_map(vs_index_t* ix, int64_t row_base, int64_t row_stride) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (row_base < 0 || row_stride < 1 || row_stride > 65536) return fail(VS_ERR_ARG, "need row_base >= 0 and 1 <= row_stride <= 65536");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  ix->row_base = row_base;
+  ix->row_stride = row_stride;
   return VS_OK;
 }
 
@@ -769,7 +781,7 @@ namespace {
 int exchange_ready(vs_index* ix, int k) {
   if (!ix->xc.local || !ix->xc.attached) return fail(VS_ERR_ARG, "exchange not created/attached");
   if (k <= 0 || k > ix->xc.kmax) return fail(VS_ERR_UNSUPPORTED, "k=%d exceeds the exchange's k_max=%d", k, ix->xc.kmax);
-  if (ix->row_base < 0 || ix->row_base + ix->n > 0xFFFFFFF0LL)
+  if (ix->row_base < 0 || ix->row_base + ix->n * ix->row_stride > 0xFFFFFFF0LL)
     return fail(VS_ERR_UNSUPPORTED, "sharded queries need global rows < 2^32");
   return VS_OK;
 }
@@ -936,6 +948,7 @@ int vs_filter_sweep_dev(vs_index_t* ix, const float* prompts_dev, int F, float t
   ta.ld_elems = ix->ld;
   ta.n_rows = ix->n;
   ta.row_base = ix->row_base;
+  ta.row_stride = ix->row_stride;
   CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(F, ix->dim, 1, ix->sm_count, ix->n)));
   CU(vs::launch_tensor_filter(ta, prompts_dev, F, tau, ix->d_tensor.p, out_bits_dev, vs_filter_words(ix), ix->sm_count,
                               pick_stream(ix, stream)));
@@ -984,6 +997,7 @@ int vs_dedup_dev(vs_index_t* ix, int64_t row_lo, int64_t row_hi, float tau, int6
   ta.ld_elems = ix->ld;
   ta.n_rows = ix->n;
   ta.row_base = ix->row_base;
+  ta.row_stride = ix->row_stride;
   CU(ix->d_tensor.reserve(vs::tensor_workspace_bytes(128, ix->dim, 1, ix->sm_count, ix->n)));
   CU(vs::launch_tensor_dedup(ta, row_lo, row_hi, tau, cap, out_i_dev, out_j_dev, out_score_dev, out_count_dev,
                              ix->d_tensor.p, ix->sm_count, st));

@@ -47,6 +47,7 @@ struct TcParams {
   uint64_t req[kMaskWords];
   int use_mask;
   int64_t row_base;
+  int64_t row_stride;
   uint32_t n_rows;
   uint32_t n_tiles;        // ceil(n_rows / BN)
   int kb_count;            // ceil(dim / 64)
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   } else {
                     const unsigned long long slot = atomicAdd(p.out_count, 1ull);
                     if ((int64_t)slot < p.cap) {
-                      p.out_i[slot] = (int64_t)a_global + p.row_base;
-                      p.out_j[slot] = (int64_t)row + p.row_base;
+                      p.out_i[slot] = (int64_t)a_global * p.row_stride + p.row_base;
+                      p.out_j[slot] = (int64_t)row * p.row_stride + p.row_base;
                       p.out_score[slot] = s;
                     }
                   }
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
         for (int j = 0; j < KL; ++j) {
           p.part_s[base + j] = top.s[j];
-          p.part_r[base + j] = top.r[j] == kEmptyRow ? -1 : (int64_t)top.r[j] + p.row_base;
+          p.part_r[base + j] = top.r[j] == kEmptyRow ? -1 : (int64_t)top.r[j] * p.row_stride + p.row_base;
         }
       }
     }
@@ -934,6 +935,7 @@ static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   }
   if (!a.mask) p.use_mask = 0;
   p.row_base = a.row_base;
+  p.row_stride = a.row_stride;
   p.n_rows = (uint32_t)a.n_rows;
   p.n_tiles = (uint32_t)((a.n_rows + pl.BN - 1) / pl.BN);
   p.kb_count = pl.kb_count;

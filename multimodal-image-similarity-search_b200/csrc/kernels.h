@@ -39,6 +39,7 @@ struct ScanArgs {
   int64_t ld_bytes;          // row pitch in bytes (multiple of 16)
   int64_t n_rows;
   int64_t row_base;
+  int64_t row_stride = 1;    // reported row = row_base + local row * row_stride (striped shards)
   // workspace (device): partial lists [B][grid][k], tickets [B]
   float* part_s;
   uint32_t* part_r;
@@ -69,7 +70,7 @@ cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstri
                             float* out_s, int64_t* out_r, cudaStream_t st);
 // exact top-k (k <= 1024) of materialised scores [B][n] -> [B][k]; workspace: see select_workspace_bytes
 size_t select_workspace_bytes(int B);
-cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, void* workspace,
+cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, int64_t row_stride, void* workspace,
                           float* out_s, int64_t* out_r, cudaStream_t st);
 
 // ---- K2/K3/K4 tcgen05 kernels (bf16 storage) -------------------------------------------------
@@ -82,6 +83,7 @@ struct TensorArgs {
   int64_t ld_elems;
   int64_t n_rows;
   int64_t row_base;
+  int64_t row_stride = 1;
 };
 // queries: f32 [B][dim] raw (normalised + rounded to bf16 on device into q_bf16 workspace)
 size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count, int64_t n_rows);

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) select_compact_kernel(const float* __restrict__ scores, int64_t n, SelectState* st,
-                                                             int k, int64_t row_base, float* __restrict__ out_s,
+                                                             int k, int64_t row_base, int64_t row_stride, float* __restrict__ out_s,
                                                              int64_t* __restrict__ out_r) {
   __shared__ int s_last;
   __shared__ unsigned long long keys[kMaxK];
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256) select_compact_kernel(const float* __rest
     if (e < (int)k_eff) {
       const unsigned long long key = keys[e];
       v = key_score((uint32_t)(key >> 32));
-      if (v != VS_NEG_INF) r = (int64_t)(0xFFFFFFFFu - (uint32_t)key) + row_base;
+      if (v != VS_NEG_INF) r = (int64_t)(0xFFFFFFFFu - (uint32_t)key) * row_stride + row_base;
     }
     out_s[(size_t)blockIdx.y * k + e] = v;
     out_r[(size_t)blockIdx.y * k + e] = r;
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) select_compact_kernel(const float* __rest
   }
 }
 
-cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, void* workspace,
+cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, int64_t row_stride, void* workspace,
                           float* out_s, int64_t* out_r, cudaStream_t st) {
   if (k > kMaxK || k <= 0 || n <= 0 || n > 0xFFFFFFF0LL) return cudaErrorInvalidValue;
   SelectState* ss = static_cast<SelectState*>(workspace);
@@ -458,7 +458,7 @@ cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t 
   const int shifts[6] = {53, 42, 32, 21, 10, 0};
   const int bits[6] = {11, 11, 10, 11, 11, 10};
   for (int pass = 0; pass < 6; ++pass) select_hist_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, ss, shifts[pass], bits[pass]);
-  select_compact_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, ss, k, row_base, out_s, out_r);
+  select_compact_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, ss, k, row_base, row_stride, out_s, out_r);
   count_launch(8);
   return cudaGetLastError();
 }

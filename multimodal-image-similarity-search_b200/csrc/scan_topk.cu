@@ -59,6 +59,7 @@ struct ScanKernelParams {
   int64_t* out_r;
   float* scores_full;
   int64_t row_base;
+  int64_t row_stride;
   uint32_t n_rows;
   uint32_t n_tiles;
   int dim;
@@ -79,18 +80,19 @@ __device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<
   if (p.xg.G > 0) {
 #pragma unroll
     for (int m = 0; m < ML; ++m)
-      if (top.r[m] != kEmptyRow) top.r[m] += (uint32_t)p.row_base;   // global rows < 2^32 (checked on the host)
+      if (top.r[m] != kEmptyRow) top.r[m] = top.r[m] * (uint32_t)p.row_stride + (uint32_t)p.row_base;   // global rows < 2^32 (checked on the host)
     xchg_push(p.xg, top, p.xg.slot0 + qi, k, lane);
     if (p.xg.push_only) return;   // vs_exchange_collect_dev merges the whole epoch later
     xchg_wait_merge(p.xg, top, p.xg.slot0 + qi, k, lane);
   }
   const int64_t add = p.xg.G > 0 ? 0 : p.row_base;
+  const int64_t mul = p.xg.G > 0 ? 1 : p.row_stride;
   for (int e = lane; e < k; e += 32) {
 #pragma unroll
     for (int m = 0; m < ML; ++m)
       if ((e >> 5) == m) {
         p.out_s[(size_t)qi * k + e] = top.s[m];
-        p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] + add;
+        p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] * mul + add;
       }
   }
 }
@@ -373,6 +375,7 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.out_r = a.out_r;
   p.scores_full = a.scores_full;
   p.row_base = a.row_base;
+  p.row_stride = a.row_stride;
   p.n_rows = (uint32_t)a.n_rows;
   p.n_tiles = (uint32_t)((a.n_rows + R - 1) / R);
   p.dim = a.dim;

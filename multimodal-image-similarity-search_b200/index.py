@@ -48,7 +48,8 @@ def _stream_ptr(stream) -> int:
 
 
 class DeviceIndex:
-    def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 0, row_base: int = 0):
+    def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 0, row_base: int = 0,
+                 row_stride: int = 1):
         self._lib = N.load()
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
@@ -56,8 +57,8 @@ class DeviceIndex:
         h = C.c_void_p()
         N.check(self._lib.vs_create(self.device, self.dim, _DTYPES[dtype], int(capacity), C.byref(h)))
         self._h = h
-        if row_base:
-            self.set_row_base(row_base)
+        if row_base or row_stride != 1:
+            self.set_row_map(row_base, row_stride)
 
     # -- lifecycle ---------------------------------------------------------------------
     def close(self):
@@ -86,6 +87,10 @@ class DeviceIndex:
 
     def set_row_base(self, row_base: int):
         N.check(self._lib.vs_set_row_base(self._h, int(row_base)))
+
+    def set_row_map(self, row_base: int, row_stride: int = 1):
+        """Reported row = row_base + local row * row_stride (striped shards: (shard, G))."""
+        N.check(self._lib.vs_set_row_map(self._h, int(row_base), int(row_stride)))
 
     # -- ingest / maintenance ------------------------------------------------------------
     def add(self, rows) -> int:

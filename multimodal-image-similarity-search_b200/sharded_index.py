@@ -11,9 +11,9 @@ Layout: global row g lives on shard ``g % G`` at local row ``g // G`` (appends s
 any directory).  ``remove(row)`` keeps the Collection's contract (the LAST global row moves into the
 hole): the last row's vector and filter bits are fetched from its shard, written over the deleted
 row's slot on ITS shard (``vs_set_row_host``), and the last row's shard shrinks by one.
-Shards report ``(shard << 28) | local`` so that rows stay unique and < 2^32 through the device-side
-exchange/merge; rank 0 translates to global rows.  (Exact score ties between different shards are
-therefore ordered by shard, not by global row -- "identical top-k sets modulo ties".)
+Every shard's kernels report TRUE global rows (``vs_set_row_map(shard, G)``: reported row =
+shard + local * G), so the device-side exchange/merge orders exact score ties by global row and the
+answer is identical to a single index holding all rows.
 
 Every operation is a collective driven by rank 0: a small header goes out with
 ``broadcast_object_list``, array payloads with ``broadcast``; query results come back through the
@@ -26,8 +26,6 @@ from __future__ import annotations
 from typing import Callable, Optional, Sequence
 
 import numpy as np
-
-SHARD_SHIFT = 28          # local rows per shard < 2^28 (268M): 8 shards stay below 2^31
 
 
 class ShardedIndex:
@@ -47,7 +45,7 @@ class ShardedIndex:
         self.comm_device = comm_device or ("cuda:%d" % self.device if dist.get_backend(group) == "nccl" else "cpu")
         if index_factory is None:
             from .index import DeviceIndex as index_factory
-        self.local = index_factory(self.dim, self.dtype, self.device, 0, self.rank << SHARD_SHIFT)
+        self.local = index_factory(self.dim, self.dtype, self.device, 0, self.rank, self.world)   # row map (shard, G)
         if searcher_factory is None:
             from .sharded import ShardedSearcher
 
@@ -180,17 +178,12 @@ class ShardedIndex:
         self._header({"op": "add", "n": int(a.shape[0])})
         return self._do_add(self._bcast(a, a.shape, np.float32))
 
-    def _translate(self, r: np.ndarray) -> np.ndarray:
-        out = np.where(r >= 0, (r & ((1 << SHARD_SHIFT) - 1)) * self.world + (r >> SHARD_SHIFT), -1)
-        return out.astype(np.int64)
-
     def query(self, q, k: int, require_bits: Optional[Sequence[int]] = None, mode: str = "auto"):
         self._require_front()
         a = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
         self._header({"op": "query", "B": int(a.shape[0]), "k": int(k), "bits": require_bits})
         s, r = self._do_query(self._bcast(a, a.shape, np.float32), int(k), require_bits)
-        s, r = s.cpu().numpy(), r.cpu().numpy()
-        return s, self._translate(r)
+        return s.cpu().numpy(), r.cpu().numpy().astype(np.int64)
 
     def query_dev(self, q, k: int, out_scores=None, out_rows=None, require_bits=None, mode: str = "auto", stream=None):
         """Device-tensor flavour of :meth:`query` (the queries are re-broadcast to the other ranks)."""

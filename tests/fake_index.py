@@ -7,8 +7,9 @@ from oracle import cosine_oracle as O
 
 
 class FakeIndex:
-    def __init__(self, dim, dtype="f32", device=0, capacity=0, row_base=0):
+    def __init__(self, dim, dtype="f32", device=0, capacity=0, row_base=0, row_stride=1):
         self.dim, self.dtype, self.row_base = dim, ("bf16" if dtype in ("bf16", "bfloat16") else "f32"), row_base
+        self.row_stride = row_stride
         self.X = np.zeros((0, dim), np.float32)
         self.bits = []
         self.closed = False
@@ -58,7 +59,7 @@ class FakeIndex:
         s, r = O.cosine_topk(q, self.X, k, corpus_dtype=self.dtype, valid=valid)
         out_s = np.full((q.shape[0], k), -np.inf, np.float32)
         out_r = np.full((q.shape[0], k), -1, np.int64)
-        out_s[:, :s.shape[1]], out_r[:, :r.shape[1]] = s, r + self.row_base
+        out_s[:, :s.shape[1]], out_r[:, :r.shape[1]] = s, r * self.row_stride + self.row_base
         return out_s, out_r
 
     def query_multimodal(self, img, txt, w, k, require_bits=None, mode="auto"):

@@ -93,6 +93,9 @@ def main():
         sh.serve()
     else:
         n2 = 30_001
+        X = X[:n2].copy()
+        X[n2 - 1] = X[7]                               # exact tie across shards: ordered by global row, like one index
+        Q = np.concatenate([Q[:5], X[7:8]])
         ids = [f"img_{i:05x}" for i in range(n2)]
         metas = [{"filename": f"{i}.jpg", "filter_results_json": '{"is it red?": "%s"}' % ("yes" if i % 4 == 0 else "no")}
                  for i in range(n2)]

@@ -210,3 +210,33 @@ def test_device_query_api_and_launch_counter(gpu):
     assert gpu.launch_count() == before + 1               # ONE fused kernel for the whole batch
     _check(s.cpu().numpy(), r.cpu().numpy() - 1_000_000, Q, X, 10, "bf16")
     ix.close()
+
+
+@pytest.mark.parametrize("k", [10, 200, 1000])
+def test_two_shards_merged_equal_one_index(gpu, k):
+    """The all-gather arm of the sharded query (k > 128 always takes it): per-shard top-k with shard
+    row bases (contiguous shards) or the ShardedIndex's row map (striped shards) merged by K5 == one index."""
+    import torch
+    rng = np.random.default_rng(k)
+    n, d, B = 30_001, 512, 6
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    whole = gpu.DeviceIndex(d, "bf16")
+    whole.add(X)
+    s0, r0 = whole.query(Q, k, mode="scan")
+    qd = torch.from_numpy(Q).cuda()
+    for striped in (False, True):
+        cs, cr, shards = [], [], []
+        for g in range(2):
+            # contiguous shards (row_base) or row-striped shards (ShardedIndex: reported row = g + local * 2)
+            ix = gpu.DeviceIndex(d, "bf16", row_base=g, row_stride=2) if striped else \
+                gpu.DeviceIndex(d, "bf16", row_base=g * 15_001)
+            ix.add(X[g::2] if striped else X[g * 15_001:(g + 1) * 15_001])
+            s, r = ix.query_dev(qd, k, mode="scan")
+            cs.append(s); cr.append(r); shards.append(ix)
+        s, r = shards[0].merge_dev(torch.stack(cs), torch.stack(cr))
+        s, r = s.cpu().numpy(), r.cpu().numpy()
+        assert np.array_equal(r, r0) and np.array_equal(s, s0)
+        for ix in shards:
+            ix.close()
+    whole.close()

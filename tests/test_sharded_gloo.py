@@ -153,6 +153,7 @@ def _service_worker(rank, world, port, out):
     many = C.Collection("many", {"hnsw:space": "cosine"}, index=sh)
     rng = np.random.default_rng(3)
     X = rng.standard_normal((61, 24)).astype(np.float32)
+    X[50] = X[3]                                   # an exact tie between rows on different shards (3 % 3 != 50 % 3)
     ids = [f"img_{i:02d}" for i in range(61)]
     metas = [{"filename": f"{i}.jpg", "filter_results_json": '{"is it red?": "%s"}' % ("yes" if i % 3 == 0 else "no")}
              for i in range(61)]
@@ -161,7 +162,8 @@ def _service_worker(rank, world, port, out):
         col.add(ids=ids[40:], embeddings=X[40:], metadatas=metas[40:])        # second batch: striping continues
         col.add(ids=ids[:2], embeddings=X[:2])                                 # existing ids are skipped
     assert many.count() == one.count() == 61 and len(sh) == 61
-    Q = rng.standard_normal((5, 24)).astype(np.float32)
+    Q = np.concatenate([rng.standard_normal((4, 24)).astype(np.float32), X[3:4]])
+    assert many.query(query_embeddings=Q[4:5].tolist(), n_results=2)["ids"] == [[ids[3], ids[50]]]   # tie: lower global row first
 
     def same(**kw):
         a, b = one.query(query_embeddings=Q.tolist(), **kw), many.query(query_embeddings=Q.tolist(), **kw)
