@@ -97,11 +97,26 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         if self.world_size > 8:
             raise ValueError("the peer exchange supports at most 8 ranks (one NVSwitch domain)")
-        mine = index.exchange_create(self.world_size, self.rank, self.b_max, self.k_max)
+        # Set-up is failure-atomic across ranks: every rank always takes part in both object
+        # all-gathers, so a rank that cannot create or map a buffer makes ALL ranks raise together
+        # (the caller can then fall back to exchange="nccl" on every rank) instead of hanging its peers.
+        mine, err = None, None
+        try:
+            mine = index.exchange_create(self.world_size, self.rank, self.b_max, self.k_max)
+        except Exception as e:                        # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"
         handles = [None] * self.world_size
         dist.all_gather_object(handles, mine, group=group)       # also orders "every buffer is zeroed"
-        index.exchange_attach(ipc_handles=handles)
-        dist.barrier(group=group)                                # every rank has mapped every buffer
+        if all(h is not None for h in handles):
+            try:
+                index.exchange_attach(ipc_handles=handles)
+            except Exception as e:                    # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
+        errs = [None] * self.world_size
+        dist.all_gather_object(errs, err, group=group)           # every rank has mapped every buffer (or reports why not)
+        bad = {r: e for r, e in enumerate(errs) if e is not None}
+        if bad:
+            raise RuntimeError(f"peer exchange unavailable: {bad}")
 
     def search(self, q, k: int, mode: str = "auto", out_scores=None, out_rows=None, require_bits=None):
         return self.index.query_sharded_dev(q, k, out_scores=out_scores, out_rows=out_rows, mode=mode,

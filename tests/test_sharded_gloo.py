@@ -207,3 +207,43 @@ def test_world_size_3_sharded_collection_service():
         p.join(150)
         assert p.exitcode == 0
     assert out.get(timeout=5) == "ok"
+
+
+def _px_fail_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmiss_b200.sharded import PeerExchange
+
+    class Stub:                                            # rank 1 cannot create its buffer
+        device = 0
+
+        def exchange_create(self, g, r, b, k):
+            if r == 1:
+                raise MemoryError("no memory for the exchange buffer")
+            return b"h" * 64
+
+        def exchange_attach(self, ipc_handles=None, peer_ptrs=None):
+            raise AssertionError("must not attach when a peer has no buffer")
+    try:
+        PeerExchange(Stub(), None, 8, 8)
+        out.put(f"rank {rank}: no error")
+    except RuntimeError as e:
+        assert "MemoryError" in str(e)
+        out.put("raised")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_peer_exchange_setup_fails_on_every_rank_together():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_px_fail_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    assert [out.get(timeout=5), out.get(timeout=5)] == ["raised", "raised"]
