@@ -405,14 +405,52 @@ def run_ours(args):
         barrier()
         batched_ms = b0.elapsed_time(b1) / 5
 
+    # ---- extras (not the headline): BASELINE configs 4 and 5 on this rank's shard -------------------------
+    filter_ms, dedup_ms, dedup_rows, dedup_dim = 0.0, 0.0, 0, 768
+    if args.dtype == "bf16" and args.filters > 0:
+        gf = torch.Generator(device=dev).manual_seed(4343)
+        prompts = torch.randn((args.filters, args.dim), generator=gf, device=dev)
+        fbits = torch.zeros((args.filters, ix.filter_words()), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            ix.filter_sweep_dev(prompts, 0.103, out_bits=fbits)           # ~1 % of random 512-d rows pass
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(5):
+            ix.filter_sweep_dev(prompts, 0.103, out_bits=fbits)
+        f1.record()
+        barrier()
+        filter_ms = f0.elapsed_time(f1) / 5
+        del fbits
+    if args.dtype == "bf16" and args.dedup_rows > 0 and G == 1:
+        dedup_rows = args.dedup_rows
+        dx = M.DeviceIndex(dedup_dim, "bf16", device=local_rank, capacity=dedup_rows)
+        for c0 in range(0, dedup_rows, chunk):
+            n = min(chunk, dedup_rows - c0)
+            gen.manual_seed(777 + c0)
+            dx.add(torch.nn.functional.normalize(torch.randn((n, dedup_dim), generator=gen, device=dev), dim=1))
+        cap = 1 << 16
+        oi = torch.empty(cap, dtype=torch.int64, device=dev); oj = torch.empty(cap, dtype=torch.int64, device=dev)
+        osc = torch.empty(cap, dtype=torch.float32, device=dev); cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        dx.dedup_dev(0.95, 0, dedup_rows, oi, oj, osc, cnt)
+        torch.cuda.synchronize()
+        d0 = torch.cuda.Event(enable_timing=True); d1 = torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(2):
+            dx.dedup_dev(0.95, 0, dedup_rows, oi, oj, osc, cnt)
+        d1.record()
+        torch.cuda.synchronize()
+        dedup_ms = d0.elapsed_time(d1) / 2
+        dx.close()
+
     # ---- reduce over ranks (max time) -----------------------------------------------------------------
     xerr = ix.exchange_error() if p2p else 0
     if xerr:
         raise SystemExit(f"bench.py: peer exchange timed out on rank {rank} (results invalid)")
-    tvals = torch.tensor([elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s], dtype=torch.float64, device=dev)
+    tvals = torch.tensor([elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s, filter_ms], dtype=torch.float64, device=dev)
     if G > 1:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
-    elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s = tvals.tolist()
+    elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s, filter_ms = tvals.tolist()
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
@@ -445,6 +483,21 @@ def run_ours(args):
                                "ms_per_batch": batched_ms, "qps": args.batch / (batched_ms / 1e3), "tflops": tf,
                                "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
                                "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"]}
+        if filter_ms > 0:
+            tf = 2.0 * args.filters * args.rows * args.dim / (filter_ms / 1e3) / 1e12
+            fbytes = args.rows * args.dim * 2 + args.filters * args.rows / 8
+            line["filter_sweep"] = {"workload": f"{args.filters} filter prompts x {args.rows} rows, cos >= 0.103 -> bit mask "
+                                                "(tcgen05, no exchange: mask rows are shard-local)",
+                                    "ms": filter_ms, "tflops": tf, "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
+                                    "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"],
+                                    "gb_per_s": fbytes / (filter_ms / 1e3) / 1e9,
+                                    "frac_of_hbm": fbytes / (filter_ms / 1e3) / 1e9 / G / peaks["hbm_gbs"]}
+        if dedup_ms > 0:
+            tf = float(dedup_dim) * dedup_rows * (dedup_rows - 1) / (dedup_ms / 1e3) / 1e12
+            line["dedup"] = {"workload": f"all pairs cos >= 0.95 over {dedup_rows} x {dedup_dim} bf16 rows (tcgen05; "
+                                         "useful-triangle flops; the 8-GPU 2M-row run is tools/bench_dedup_sharded.py)",
+                             "ms": dedup_ms, "tflops": tf, "frac_of_bf16_burst": tf / peaks["bf16_tflops"],
+                             "frac_of_bf16_sustained": tf / peaks["bf16_tflops_sustained"]}
         if G == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_qps(args.rows, args.dim, k, budget_s=args.cpu_budget)
         print(json.dumps(line))
@@ -465,6 +518,8 @@ def main():
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--queries", type=int, default=32, help="single-query scans per step")
     ap.add_argument("--batch", type=int, default=1024, help="batched tensor-path extra (0 = skip)")
+    ap.add_argument("--filters", type=int, default=256, help="filter-sweep extra: number of prompts (0 = skip)")
+    ap.add_argument("--dedup-rows", type=int, default=200_000, help="dedup extra (N=1 only): rows x 768 (0 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: candidate exchange fused into the query kernel over NVLink peer memory, or NCCL all-gather")
     ap.add_argument("--hnsw-rows", type=int, default=20_000,

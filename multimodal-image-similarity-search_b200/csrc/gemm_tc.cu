@@ -857,8 +857,7 @@ static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, c
   auto kern = tc_kernel<MODE, BN, KL, C, CG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters_wanted * C), 1, 1);
   cfg.blockDim = dim3(kTcThreads, 1, 1);
   cfg.dynamicSmemBytes = pl.smem;
@@ -883,8 +882,7 @@ static int max_clusters(const TcPlan& pl, int sm_count) {
     cudaGetLastError();
     return sm_count / C;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(sm_count / C * C), 1, 1);
   cfg.blockDim = dim3(kTcThreads, 1, 1);
   cfg.dynamicSmemBytes = pl.smem;
