@@ -124,10 +124,9 @@ def run_reference(args):
     hnsw = None
     if args.hnsw_rows > 0:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import hnsw_recall
-            hnsw = [hnsw_recall.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=True),
-                    hnsw_recall.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=False)]
+            from oracle import hnsw_oracle
+            hnsw = [hnsw_oracle.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=True),
+                    hnsw_oracle.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=False)]
         except Exception as e:                        # noqa: BLE001 -- gcc missing etc.: report, do not fail the arm
             hnsw = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     line = {

@@ -88,3 +88,46 @@ def recall_at_k(approx_ids: np.ndarray, exact_ids: np.ndarray) -> float:
     k = exact_ids.shape[1]
     hit = sum(len(set(a.tolist()) & set(e.tolist())) for a, e in zip(approx_ids, exact_ids))
     return hit / (k * exact_ids.shape[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# the number the spec asks for: recall@k of this index against the exact result, with its CPU rates
+# (called by tests/ and by `bench.py --impl reference`)
+# ------------------------------------------------------------------------------------------------
+import time  # noqa: E402
+
+from . import cosine_oracle as O  # noqa: E402
+
+
+def synth(rows, dim, queries, clustered, seed=0):
+    rng = np.random.default_rng(seed)
+    if not clustered:
+        X = rng.standard_normal((rows, dim), dtype=np.float32)
+        Q = rng.standard_normal((queries, dim), dtype=np.float32)
+    else:
+        nc = max(16, rows // 500)
+        c = rng.standard_normal((nc, dim), dtype=np.float32)
+        X = c[rng.integers(0, nc, rows)] + 0.6 * rng.standard_normal((rows, dim), dtype=np.float32)
+        Q = c[rng.integers(0, nc, queries)] + 0.6 * rng.standard_normal((queries, dim), dtype=np.float32)
+    return O.normalize_rows(X), O.normalize_rows(Q)
+
+
+def measure(rows, dim, queries, k, clustered, efs=(10, 100), M=16, efc=100):
+    X, Q = synth(rows, dim, queries, clustered)
+    t0 = time.perf_counter()
+    ix = HnswIndex(dim, rows, M=M, ef_construction=efc)
+    ix.add(X)
+    t_build = time.perf_counter() - t0
+    exact = np.stack([np.argsort(-(X @ q), kind="stable")[:k] for q in Q])
+    out = {"index": f"HNSW M={M} ef_construction={efc} (chromadb defaults), cosine, single thread",
+           "rows": rows, "dim": dim, "queries": queries, "k": k,
+           "data": "clustered unit-norm" if clustered else "uniform random unit-norm",
+           "build_s": round(t_build, 2), "build_rows_per_s": round(rows / t_build, 1)}
+    for ef in efs:
+        t0 = time.perf_counter()
+        ids, _ = ix.search(Q, k, ef=ef)
+        dt = time.perf_counter() - t0
+        out[f"recall@{k}_ef{ef}"] = round(recall_at_k(ids, exact), 4)
+        out[f"qps_ef{ef}"] = round(queries / dt, 1)
+    ix.close()
+    return out

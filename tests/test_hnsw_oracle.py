@@ -1,6 +1,6 @@
 """CPU: the hnswlib restatement (oracle/hnsw_oracle.c) behaves like an HNSW index should -- exact on
 small sets when the beam covers them, high recall on clustered data at chromadb's defaults, monotone
-in ef -- so the recall-vs-exact number reported by tools/hnsw_recall.py means something."""
+in ef -- so the recall-vs-exact number reported by bench.py's reference arm means something."""
 import numpy as np
 
 from oracle import cosine_oracle as O
@@ -52,3 +52,10 @@ def test_fewer_points_than_k_and_full_index():
         raise AssertionError("add to a full index must fail")
     except ValueError:
         pass
+
+
+def test_measure_reports_recall_and_rates():
+    from oracle import hnsw_oracle
+    out = hnsw_oracle.measure(1500, 32, 40, 10, clustered=True)
+    assert 0.5 < out["recall@10_ef10"] <= out["recall@10_ef100"] + 1e-9 <= 1.0 + 1e-9
+    assert out["qps_ef10"] > 0 and out["build_rows_per_s"] > 0
