@@ -679,6 +679,8 @@ size_t vs_exchange_bytes(int B_max, int k_max, int G) {
   return vs::exchange_bytes(B_max, k_max, G);
 }
 
+static int exchange_create_locked(vs_index* ix, int G, int rank, int B_max, int k_max);
+
 int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
   if (!ix) return fail(VS_ERR_ARG, "index is NULL");
   if (G <= 0 || G > vs::kMaxPeers || rank < 0 || rank >= G)
@@ -688,6 +690,16 @@ int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max) {
   std::lock_guard<std::mutex> lk(ix->mu);
   if (ix->xc.local) return fail(VS_ERR_ARG, "exchange already created for this index");
   DeviceGuard g(ix->device);
+  const int rc = exchange_create_locked(ix, G, rank, B_max, k_max);
+  if (rc != VS_OK && ix->xc.local) {   // roll back: a later retry (or the NCCL arm) starts clean
+    cudaFree(ix->xc.local);
+    cudaGetLastError();
+    ix->xc.local = nullptr;
+  }
+  return rc;
+}
+
+static int exchange_create_locked(vs_index* ix, int G, int rank, int B_max, int k_max) {
   const size_t bytes = vs::exchange_bytes(B_max, k_max, G);
   // plain cudaMalloc (not a pool allocation): required for cudaIpcGetMemHandle
   CU(cudaMalloc(&ix->xc.local, bytes));
