@@ -61,7 +61,10 @@ struct TcParams {
   unsigned long long* dbg; // VS_TC_DEBUG_COUNT=1: [groups, slow-path entries, lanes that hit, inserts]
   const float* gmin;       // [ceil(n_rows/32)] (1 - 2^-20) * min row norm of each 32-row group (+inf if empty)
   // top-k
-  uint32_t* gbound;        // [Bp] orderable key of the best known lower bound on each query's k-th score
+  uint32_t* gbound;        // [Bp][pool stride] orderable keys: per query k class maxima (row % k) over everything ANY
+                           // slice / epilogue half has inserted; their minimum is a lower bound on the k-th score
+  int k_real;              // slots of the pool in use (= k)
+  int pool_mode;           // 1: shared pool (default); 0: one key per query = max of the lists' own k-th scores
   float* part_s;           // [n_slices][2][Bp][KL]  (2 = the two epilogue halves)
   int64_t* part_r;
   int Bp;                  // C * 128
@@ -277,6 +280,30 @@ struct ThreadTopK {
   }
 };
 
+// ---- per-query shared pool of k class maxima (orderable keys) -------------------------------------
+// Every epilogue thread keeps its own list for (slice, half); alone, each list only knows the k-th
+// best of ITS rows, so all ~30 lists of a query warm up separately and the exact slow path runs for
+// a third of the 32-row groups.  The pool has k slots; slot c holds the best score inserted so far, by
+// ANY list, among corpus rows with row % k == c.  The k slots are scores of k DISTINCT rows, so their
+// minimum is a lower bound on the query's final k-th best score -- and it reflects every row processed
+// so far by every slice, not one list's share.  Updating it is one fire-and-forget atomicMax (RED):
+// no read-modify-write loop, no latency on the insert path; reading it is 3 vector loads per tile.
+__host__ __device__ constexpr int pool_stride(int KL) { return KL <= 12 ? 12 : 32; }   // 16-byte aligned rows
+template <int KLP>
+__device__ __forceinline__ uint32_t pool_min(const uint32_t* pool, int k, int& idx) {
+  uint32_t mn = 0xFFFFFFFFu;
+  idx = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < KLP / 4; ++j4) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(pool + 4 * j4));
+    if (4 * j4 < k && a < mn) { mn = a; idx = 4 * j4; }
+    if (4 * j4 + 1 < k && b < mn) { mn = b; idx = 4 * j4 + 1; }
+    if (4 * j4 + 2 < k && c < mn) { mn = c; idx = 4 * j4 + 2; }
+    if (4 * j4 + 3 < k && d < mn) { mn = d; idx = 4 * j4 + 3; }
+  }
+  return mn;
+}
 __device__ __forceinline__ bool tc_mask_ok(const uint64_t* mask, uint32_t row, const uint64_t* req) {
   const uint64_t* m = mask + (size_t)row * kMaskWords;
   bool ok = true;
@@ -513,11 +540,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // scoring strictly below it cannot be in the global top-k.
       uint32_t* gb_ptr = nullptr;
       float published = VS_NEG_INF;
-      if (MODE == kModeTopK) gb_ptr = p.gbound + (size_t)ablock * kTcM + m_local;
+      constexpr int KLP = pool_stride(KL);
+      if (MODE == kModeTopK) gb_ptr = p.gbound + ((size_t)ablock * kTcM + m_local) * KLP;
       for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t acc = tile_ctr % ACC;
         float gb = VS_NEG_INF;
-        if (MODE == kModeTopK && p.debug_noepi != 4) gb = key_score(*reinterpret_cast<volatile uint32_t*>(gb_ptr));
+        if (MODE == kModeTopK && p.debug_noepi != 4) {
+          int unused;
+          gb = key_score(p.pool_mode ? pool_min<KLP>(gb_ptr, p.k_real, unused) : *reinterpret_cast<volatile uint32_t*>(gb_ptr));
+        }
         mbar_wait(&tfull[acc], (tile_ctr / ACC) & 1);
         tc_fence_after();
         const uint32_t ib = tile_ctr % kInvRing;
@@ -529,6 +560,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
           const uint32_t rg = row0 + g * 32;
+          if (MODE == kModeTopK && p.pool_mode && t - t0 < 2u && p.debug_noepi != 4) {
+            // warm-up: the pool fills within the first groups of an item; pick the bound up per group
+            int unused;
+            gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
+          }
           const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
           const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * BN + g * 32);   // staged by the producer
           if (MODE == kModeFilter) {
@@ -617,7 +653,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   if (MODE == kModeTopK) {
                     if (s > top.threshold()) {
                       if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
-                      if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) top.insert(s, row);
+                      if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) {
+                        top.insert(s, row);
+                        if (p.pool_mode && p.debug_noepi != 4) atomicMax(gb_ptr + row % (uint32_t)p.k_real, score_key(s));
+                      }
                     }
                   } else {
                     const unsigned long long slot = atomicAdd(p.out_count, 1ull);
@@ -640,7 +679,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           else mbar_arrive(&tempty[acc]);
           mbar_arrive(&iempty[ib]);
         }
-        if (MODE == kModeTopK && p.debug_noepi != 4 && top.threshold() > published) {
+        if (MODE == kModeTopK && !p.pool_mode && p.debug_noepi != 4 && top.threshold() > published) {
           published = top.threshold();
           atomicMax(gb_ptr, score_key(published));
         }
@@ -670,11 +709,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // query preparation: normalise (f32), round to bf16, zero-pad to [Bp][Dp]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int B, int dim, int Bp, int Dp,
-                                                           __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ gbound) {
+                                                           __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ gbound,
+                                                           int pool_stride_words) {
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= Bp) return;
-  if (lane == 0 && gbound) gbound[b] = score_key(VS_NEG_INF);
+  if (gbound && lane < pool_stride_words) gbound[(size_t)b * pool_stride_words + lane] = score_key(VS_NEG_INF);
   __nv_bfloat16* o = out + (size_t)b * Dp;
   if (b >= B) {
     for (int e = lane; e < Dp; e += 32) o[e] = __float2bfloat16_rn(0.f);
@@ -778,11 +818,11 @@ static TcPlan plan_for_cg(int dim, int cg_request) {
   static const int force_stream = env_int("VS_TC_ASTREAM", -1);
   const bool resident_ok = a_bytes + fixed + 2 * 128 * 128 <= (size_t)kTcSmemMax;
   pl.a_stream = force_stream >= 0 ? (force_stream != 0 || !resident_ok || stages_for(pl.BN) < 2) : 1;
-  // CTA pairs (tcgen05 cta_group::2, VS_TC_CG=2): needs streamed A, BN = 256 and an even cluster.  Opt-in:
-  // measured on B200 (profiles/r01_tensor_path.md) the pair mainloop is 4 % faster with the epilogue
-  // compiled out (1.30 vs 1.25 PFLOP/s) but 6 % slower with it (1.06 vs 1.13), because the leader's next
-  // MMA into an accumulator buffer must wait for the epilogues of BOTH CTAs (the slower of two).
-  static const int want_cg = env_int("VS_TC_CG", 1);
+  // CTA pairs (tcgen05 cta_group::2): needs streamed A, BN = 256 and an even cluster; VS_TC_CG=1 = single-CTA
+  // MMAs.  The pair mainloop is 4 % faster (1.30 vs 1.25 PFLOP/s with the epilogue compiled out) but the
+  // leader's next MMA into an accumulator buffer waits for the epilogues of BOTH CTAs, so it only pays
+  // once the top-k slow path is rare (shared pool bound): 1.147 vs 1.138 (K2), 1.02 vs 1.01 (K3).
+  static const int want_cg = env_int("VS_TC_CG", 2);
   if (pl.a_stream && pl.BN == 256 && want_cg == 2 && cg_request != 1) pl.cg = 2;
   if (pl.a_stream) {
     const size_t stride = (size_t)pl.BN * 128 / pl.cg + (size_t)kTcM * 128;
@@ -831,7 +871,7 @@ static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_cou
   w.gmin = reinterpret_cast<float*>(p + off);
   off += up((size_t)w.n_groups * 4);
   w.gbound = reinterpret_cast<uint32_t*>(p + off);
-  off += up((size_t)Bp * 4);
+  off += up((size_t)Bp * 32 * 4);   // union pool: up to 32 keys per query
   w.q = reinterpret_cast<__nv_bfloat16*>(p + off);
   off += up((size_t)Bp * pl.Dp * 2);
   w.parts = reinterpret_cast<float*>(p + off);
@@ -965,7 +1005,8 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
   __nv_bfloat16* qb = ws.q;
   float* part_s = ws.parts;
 
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb, ws.gbound);
+  const int KLP = pool_stride(KL);
+  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb, ws.gbound, KLP);
   count_launch();
   launch_gmin(a, ws, st);
 
@@ -977,7 +1018,10 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
     TcParams p;
     fill_common(p, a, plc);
     p.gmin = ws.gmin;
-    p.gbound = ws.gbound + (size_t)c0 * kTcM;
+    p.gbound = ws.gbound + (size_t)c0 * kTcM * KLP;
+    p.k_real = k;
+    static const int pool_mode = env_int("VS_TC_POOL", 1);
+    p.pool_mode = pool_mode;
     const int ncl = VS_TC_DISPATCH(max_clusters, kModeTopK, plc.BN, KL, C, cg, plc, sm_count);
     plan_slices(p, ncl);
     p.Bp = C * kTcM;
@@ -1021,7 +1065,7 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
   const int Bp = (F + kTcM - 1) / kTcM * kTcM;
   const TcWorkspace ws = carve_workspace(workspace, F, a.dim, 1, sm_count, a.n_rows);
   __nv_bfloat16* qb = ws.q;
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb, nullptr);
+  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb, nullptr, 0);
   count_launch();
   const int chunks_total = Bp / kTcM;
   for (int c0 = 0; c0 < chunks_total;) {
