@@ -319,7 +319,7 @@ __device__ __forceinline__ bool tc_mask_ok(const uint64_t* mask, uint32_t row, c
 // M = 256 MMA for both A blocks; each CTA keeps only HALF of every B tile (its BN/2 rows) in smem, so
 // per MMA a CTA reads 4 KB of A + 4 KB of B from smem instead of 4 + 8, and receives 16 + 16 KB per
 // stage instead of 16 + 32.  Accumulators stay per CTA (128 lanes x BN columns), so the epilogue is
-// unchanged.  CG = 2 implies streamed A (p.a_stream) and an even cluster size.
+// unchanged.  CG = 2 needs an even cluster size; A is streamed per stage or (when it fits) resident.
 template <int MODE, int BN, int KL, int C, int CG = 1>
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -414,9 +414,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (!p.a_stream) {
           // A block: resident for the whole item
           if (n_item > 0) mbar_wait(a_empty, (n_item - 1) & 1);
-          mbar_expect_tx(a_full, (uint32_t)p.kb_count * kABlockBytes);
-          for (int kb = 0; kb < p.kb_count; ++kb)
-            tma_load_2d(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+          if (CG == 2) {
+            // pair mode: both CTAs' A blocks are counted on the LEADER's barrier (its MMA reads both)
+            if (leader) mbar_expect_tx(a_full, 2u * (uint32_t)p.kb_count * kABlockBytes);
+            for (int kb = 0; kb < p.kb_count; ++kb)
+              tma_load_2d_cg2(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+          } else {
+            mbar_expect_tx(a_full, (uint32_t)p.kb_count * kABlockBytes);
+            for (int kb = 0; kb < p.kb_count; ++kb)
+              tma_load_2d(sA + (size_t)kb * kABlockBytes, &tmA, kb * kTcKB, a_row, a_full, pol_keep);
+          }
         }
         // L2 prefetch runs `prefetch` stages ahead of the smem ring (this CTA's part of each box)
         const uint32_t n_st = (t1 - t0) * (uint32_t)p.kb_count;
@@ -448,8 +455,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               // pair mode: the LEADER's barrier counts everything both CTAs of the pair receive for this
               // stage (2 A k-blocks + 2 half B tiles).  This CTA's part of the B tile belongs to half
               // h = rank / (C/2) of the tile and goes to every CTA of parity h (leaders hold half 0).
-              if (leader) mbar_expect_tx(&full[st], 2u * (kStageBytes + kABlockBytes));
-              tma_load_2d_cg2(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
+              if (leader) mbar_expect_tx(&full[st], 2u * (kStageBytes + (p.a_stream ? kABlockBytes : 0u)));
+              if (p.a_stream)
+                tma_load_2d_cg2(sB + (size_t)st * stage_stride + kStageBytes, &tmA, kb * kTcKB, a_row, &full[st], pol_keep);
               const uint32_t h = rank / kHalfC;
               uint8_t* dst = sB + (size_t)st * stage_stride + (size_t)(rank % kHalfC) * kPartRows * 128;
               tma_load_2d_mc_cg2(dst, &tmB, kb * kTcKB, row, &full[st], (uint16_t)(kEvenMask << h), pol_stream);
@@ -509,7 +517,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           // accumulator ready for the epilogue (pair mode: of both CTAs)
           if (CG == 2) umma_commit_mc_cg2(&tfull[acc], (uint16_t)(3u << rank)); else umma_commit(&tfull[acc]);
         }
-        if (!p.a_stream) umma_commit(a_empty);     // A block may be overwritten
+        if (!p.a_stream) {                         // A block may be overwritten (pair mode: in both CTAs)
+          if (CG == 2) umma_commit_mc_cg2(a_empty, (uint16_t)(3u << rank)); else umma_commit(a_empty);
+        }
       }
     }
     __syncwarp();
@@ -801,7 +811,10 @@ struct TcPlan {
   size_t smem;
   bool ok;
 };
-static TcPlan plan_for_cg(int dim, int cg_request) {
+// cg_request: 0 = auto, 1 / 2 = force the issue mode; +16 = prefer a resident A block in pair mode
+static bool resident_request(int env_flag, int cg_request) { return env_flag != 0 || (cg_request & 16) != 0; }
+static TcPlan plan_for_cg(int dim, int cg_request_in) {
+  const int cg_request = cg_request_in & 15;
   TcPlan pl;
   pl.kb_count = (dim + kTcKB - 1) / kTcKB;
   pl.Dp = pl.kb_count * kTcKB;
@@ -824,6 +837,22 @@ static TcPlan plan_for_cg(int dim, int cg_request) {
   // once the top-k slow path is rare (shared pool bound): 1.147 vs 1.138 (K2), 1.02 vs 1.01 (K3).
   static const int want_cg = env_int("VS_TC_CG", 2);
   if (pl.a_stream && pl.BN == 256 && want_cg == 2 && cg_request != 1) pl.cg = 2;
+  // Pair mode with a RESIDENT A block (default when >= 4 stages of 16 KB fit beside it, i.e. dim <= 512;
+  // VS_TC_ARES2=0 streams A always): each CTA then receives only its half B tile per stage (16 KB
+  // instead of 16 + 16 KB).  Measured at dim 512: K2 1.148 -> 1.172, K3 1.059 -> 1.114 (few A blocks ->
+  // clusters of 2, no wider multicast: it was at the 64 B/clk L2->SM limit), K4 1.11 -> 1.19 PFLOP/s.
+  static const int ares2 = env_int("VS_TC_ARES2", 1);
+  if (pl.cg == 2 && resident_request(ares2, cg_request_in)) {
+    const size_t stride = (size_t)pl.BN * 128 / 2;
+    const int st2 = a_bytes + fixed <= (size_t)kTcSmemMax ? (int)(((size_t)kTcSmemMax - fixed - a_bytes) / stride) : 0;
+    if (st2 >= 4) {
+      pl.a_stream = 0;
+      pl.stages = st2 > kTcMaxStages ? kTcMaxStages : st2;
+      pl.ok = true;
+      pl.smem = a_bytes + fixed + (size_t)pl.stages * stride;
+      return pl;
+    }
+  }
   if (pl.a_stream) {
     const size_t stride = (size_t)pl.BN * 128 / pl.cg + (size_t)kTcM * 128;
     pl.stages = (int)(((size_t)kTcSmemMax - fixed) / stride);

@@ -118,7 +118,8 @@ def test_filter_sweep_matches_oracle(gpu, n, d, F, tau):
     ix.close()
 
 
-@pytest.mark.parametrize("n,d", [(300, 96), (20000, 768), (9000, 512), (5000, 1024)])
+@pytest.mark.parametrize("n,d", [(300, 96), (20000, 768), (9000, 512), (5000, 1024),
+                                 (40000, 512)])      # resident-A pair mode, several work items per cluster
 def test_dedup_matches_oracle(gpu, n, d):
     if (n, d) == (300, 96):
         g = np.load(GOLD)
