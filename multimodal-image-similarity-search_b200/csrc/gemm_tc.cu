@@ -183,7 +183,14 @@ __device__ __forceinline__ void umma_commit_mc_cg2(uint64_t* bar, uint16_t mask)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  // default semantics (release at CTA scope), as for the local arrives: the only thing the leader must
+  // observe is that this warp's tcgen05.ld's have retired, which tcgen05.wait::ld + the
+  // before_thread_sync fence already order; a cluster-scope release costs a MEMBAR per tile and warp
+#ifdef VS_REMOTE_ARRIVE_RELEASE   // A/B builds only
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
