@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint64_t* ifull = a_empty + 1;             // inverse norms of a tile staged in smem: ring of kInvRing tiles
   uint64_t* iempty = ifull + kInvRing;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(iempty + kInvRing);
-  float* s_invt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kTcBarrierBytes);   // [kInvRing][BN]
+  // [kInvRing][BN inverse norms | BN/32 group min-norm bounds]
+  float* s_invt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + kTcBarrierBytes);
+  constexpr uint32_t kInvStride = BN + BN / 32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -449,8 +451,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // of stalling on L2); the array is padded past n_rows, so a whole tile is always in bounds
             const uint32_t ib = ptile % kInvRing;
             if (ptile >= (uint32_t)kInvRing) mbar_wait(&iempty[ib], (ptile / kInvRing - 1) & 1);
-            mbar_expect_tx(&ifull[ib], BN * 4);
-            bulk_g2s(s_invt + ib * BN, p.inv_norm + (size_t)t * BN, BN * 4, &ifull[ib], pol_keep);
+            mbar_expect_tx(&ifull[ib], BN * 4 + (p.gmin ? BN / 32 * 4 : 0));
+            bulk_g2s(s_invt + ib * kInvStride, p.inv_norm + (size_t)t * BN, BN * 4, &ifull[ib], pol_keep);
+            if (p.gmin) bulk_g2s(s_invt + ib * kInvStride + BN, p.gmin + (size_t)t * (BN / 32), BN / 32 * 4, &ifull[ib], pol_keep);
           }
           for (int kb = 0; kb < p.kb_count; ++kb, ++it, ++idx) {
             const int st = it % p.stages;
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
           }
           const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
-          const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * BN + g * 32);   // staged by the producer
+          const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * kInvStride + g * 32);   // staged by the producer
           if (MODE == kModeFilter) {
             float inv[32];
 #pragma unroll
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // gmin = (1 - 2^-20) * min norm of the 32 rows, so `max acc <= bound * gmin` proves that no
             // row of the group reaches `bound`; one max tree + one warp vote per 32 rows.  The exact
             // arithmetic (acc * inv_norm, as the oracle) only runs in the rare slow path.
-            const float gmn = __ldg(p.gmin + (rg >> 5));
+            const float gmn = s_invt[ib * kInvStride + BN + g];
             tmem_ld_wait();
             float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
@@ -828,7 +831,7 @@ static TcPlan plan_for_cg(int dim, int cg_request_in) {
   pl.BN = tc_block_n();
   pl.cg = 1;
   const size_t a_bytes = (size_t)pl.kb_count * kTcM * 128;
-  const size_t fixed = 1024 /*alignment slack*/ + kTcBarrierBytes + (size_t)kInvRing * 256 * 4 /*inverse-norm ring*/;
+  const size_t fixed = 1024 /*alignment slack*/ + kTcBarrierBytes + (size_t)kInvRing * (256 + 8) * 4 /*inverse-norm ring*/;
   auto stages_for = [&](int bn) { return (int)(((size_t)kTcSmemMax - fixed - a_bytes) / ((size_t)bn * 128)); };
   // Resident A needs kb_count x 16 KB of smem.  At dim 768 that left 2 x 16 KB of B stages and the
   // kernel was TMA-latency bound (dedup 200k x 768: 0.45 PFLOP/s).  Streaming the A k-block with every
