@@ -465,7 +465,11 @@ def run_ours(args):
                          "peak": peaks["hbm_gbs"], "peak_kind": peaks_kind, "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": ncu_traffic_bytes(n_local, args.dim, args.dtype),
-                         "bytes_per_launch": rows_bytes, "avg_launch_ms": scan_ms},
+                         "bytes_per_launch": rows_bytes, "avg_launch_ms": scan_ms,
+                         "note": "peak = MEASURED_PEAKS.json hbm_gbs, a read+write COPY bandwidth; this kernel only "
+                                 "reads, so frac can exceed 1 (ncu: gpu__dram_throughput 88.8 % of the DRAM peak, "
+                                 "profiles/r01c_ncu_scan_topk.txt); avg_launch_ms is per scan inside a burst of "
+                                 "back-to-back launches (consecutive scans overlap under PDL)"},
             "e2e": {"value": Q * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q * args.dim * 4,
                     "d2h_bytes_per_step": Q * k * 12, "steps": e2e_steps,
                     "path": ("vs_query_topk_host(B=%d, scan) via ctypes" % Q) if G == 1 else
