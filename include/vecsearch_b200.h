@@ -97,6 +97,8 @@ int vs_clear(vs_index_t* ix);
  *      (the predicate of backend/app/main.py:215, written by :1010-1033). */
 int vs_set_mask_bits(vs_index_t* ix, int64_t row, const uint64_t bits[VS_MASK_WORDS]);
 int vs_get_mask_bits(const vs_index_t* ix, int64_t row, uint64_t bits[VS_MASK_WORDS]);
+/* Bulk form for ingest: bits[n][VS_MASK_WORDS] for rows [first_row, first_row + n) in ONE copy. */
+int vs_set_mask_bits_range(vs_index_t* ix, int64_t first_row, int64_t n, const uint64_t* bits);
 
 /* Copy stored rows back as float32 (Collection.get(include=["embeddings"]) and persistence). */
 int vs_get_rows_host(const vs_index_t* ix, int64_t first_row, int64_t n, float* out);

@@ -43,6 +43,7 @@ SYMBOLS = {
     "vs_clear": (_i, [_p]),
     "vs_set_mask_bits": (_i, [_p, _i64, _p]),
     "vs_get_mask_bits": (_i, [_p, _i64, _p]),
+    "vs_set_mask_bits_range": (_i, [_p, _i64, _i64, _p]),
     "vs_get_rows_host": (_i, [_p, _i64, _i64, _p]),
     "vs_get_rows_dev": (_i, [_p, _i64, _i64, _p, _p]),
     "vs_query_topk_host": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),

@@ -130,6 +130,9 @@ class Collection:
 
     def _sync_filter_bits(self, row: int):
         """Mirror the row's ``filter_results_json`` "yes" answers into its device filter bits."""
+        self._index.set_filter_bits(row, self._filter_bits_of(row))
+
+    def _filter_bits_of(self, row: int) -> List[int]:
         meta = self._metas[row] or {}
         bits = []
         raw = meta.get(FILTER_JSON_KEY)
@@ -143,7 +146,7 @@ class Collection:
                     b = self._filter_bit(fname, create=True)
                     if _yes(ans):
                         bits.append(b)
-        self._index.set_filter_bits(row, bits)
+        return bits
 
     @staticmethod
     def _check_meta(m: Optional[Dict[str, Any]]):
@@ -244,16 +247,19 @@ class Collection:
             rows = rows.cpu().numpy()                 # the persistence log stores the f32 rows
         elif not isinstance(rows, np.ndarray):
             rows = _NoRows(int(rows.shape[1]))
+        with_bits = False
         for j, id_ in enumerate(ids):
             self._row_of[id_] = first + j
             self._ids.append(id_)
             self._metas.append(dict(metadatas[j]) if metadatas[j] is not None else None)
             self._docs.append(documents[j])
             if metadatas[j] and FILTER_JSON_KEY in metadatas[j]:
-                self._sync_filter_bits(first + j)
+                with_bits = True
             if log:
                 self._log_op({"op": "add", "id": id_, "dim": int(rows.shape[1]), "metadata": metadatas[j],
                               "document": documents[j]}, rows[j])
+        if with_bits:      # one bulk copy (one collective on a ShardedIndex) instead of one call per row
+            self._index.set_filter_bits_range(first, [self._filter_bits_of(first + j) for j in range(len(ids))])
         if log:
             self._log_flush()
 

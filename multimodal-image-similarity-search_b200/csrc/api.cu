@@ -537,6 +537,20 @@ int vs_set_mask_bits(vs_index_t* ix, int64_t row, const uint64_t bits[VS_MASK_WO
   return VS_OK;
 }
 
+int vs_set_mask_bits_range(vs_index_t* ix, int64_t first_row, int64_t n, const uint64_t* bits) {
+  if (!ix || (!bits && n > 0)) return fail(VS_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (first_row < 0 || n < 0 || first_row + n > ix->n) return fail(VS_ERR_ARG, "row range out of bounds");
+  if (n == 0) return VS_OK;
+  DeviceGuard g(ix->device);
+  int rc = ensure_mask(ix);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ix->mask + first_row * vs::kMaskWords, bits, (size_t)n * vs::kMaskWords * 8, cudaMemcpyHostToDevice,
+                     ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return VS_OK;
+}
+
 int vs_get_mask_bits(const vs_index_t* cix, int64_t row, uint64_t bits[VS_MASK_WORDS]) {
   vs_index* ix = const_cast<vs_index*>(cix);
   if (!ix || !bits) return fail(VS_ERR_ARG, "NULL argument");

@@ -133,6 +133,19 @@ class DeviceIndex:
     def set_filter_bits(self, row: int, bits: Sequence[int]):
         N.check(self._lib.vs_set_mask_bits(self._h, int(row), _bits_array(bits)))
 
+    def set_filter_bits_range(self, first: int, bits_lists: Sequence[Sequence[int]]):
+        """Bulk form: filter-bit indices of rows [first, first + len(bits_lists)) in one copy."""
+        n = len(bits_lists)
+        if n == 0:
+            return
+        words = np.zeros((n, N.MASK_WORDS), dtype=np.uint64)
+        for j, bits in enumerate(bits_lists):
+            for b in bits:
+                if not 0 <= b < 64 * N.MASK_WORDS:
+                    raise ValueError(f"filter bit {b} out of range [0,{64 * N.MASK_WORDS})")
+                words[j, b // 64] |= np.uint64(1 << (b % 64))
+        N.check(self._lib.vs_set_mask_bits_range(self._h, int(first), n, words.ctypes.data))
+
     def get_filter_bits(self, row: int):
         w = (C.c_uint64 * N.MASK_WORDS)()
         N.check(self._lib.vs_get_mask_bits(self._h, int(row), w))

@@ -136,6 +136,12 @@ class ShardedIndex:
             self.local.set_filter_bits(l, bits)
         return None
 
+    def _do_bits_range(self, first: int, bits_lists):
+        j0 = (self.rank - first) % self.world            # my rows are every G-th one
+        mine = bits_lists[j0::self.world]
+        if mine:
+            self.local.set_filter_bits_range((first + j0) // self.world, mine)
+
     def _dispatch(self, h):
         op = h["op"]
         if op == "add":
@@ -148,6 +154,8 @@ class ShardedIndex:
             return self._do_get_rows(h["first"], h["n"])
         if op == "bits":
             return self._do_bits(h["row"], h.get("bits"))
+        if op == "bits_range":
+            return self._do_bits_range(h["first"], h["bits"])
         if op == "clear":
             self.local.clear()
             self.n = 0
@@ -218,6 +226,12 @@ class ShardedIndex:
         self._require_front()
         self._header({"op": "bits", "row": int(row), "bits": list(bits)})
         self._do_bits(int(row), list(bits))
+
+    def set_filter_bits_range(self, first: int, bits_lists):
+        self._require_front()
+        bits_lists = [list(b) for b in bits_lists]
+        self._header({"op": "bits_range", "first": int(first), "bits": bits_lists})
+        self._do_bits_range(int(first), bits_lists)
 
     def get_filter_bits(self, row: int):
         self._require_front()

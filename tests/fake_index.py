@@ -41,6 +41,10 @@ class FakeIndex:
         self.X = self.X[:0]
         self.bits = []
 
+    def set_filter_bits_range(self, first, bits_lists):
+        for j, bits in enumerate(bits_lists):
+            self.bits[first + j] = set(bits)
+
     def set_filter_bits(self, row, bits):
         self.bits[row] = set(bits)
 
