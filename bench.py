@@ -345,6 +345,8 @@ def run_ours(args):
         for i in range(Q):
             if G == 1:
                 ix.query(q_np[i:i + 1], k, mode="scan")
+            elif p2p:
+                ix.query_sharded(q_np[i:i + 1], k, mode="scan")   # vs_query_topk_sharded_host: H2D + kernel/exchange + D2H + sync
             else:
                 qd = q_host[i:i + 1].to(dev, non_blocking=True)
                 s, r = searcher.search(qd, k)

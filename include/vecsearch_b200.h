@@ -165,6 +165,10 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
 int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B,
                           int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
 int vs_exchange_error(vs_index_t* ix);
+/* HOST-buffer flavour of vs_query_topk_sharded_dev (one call per request on every rank: pinned H2D of
+ * the replicated queries, query kernel with the fused exchange, D2H of the global result, sync). */
+int vs_query_topk_sharded_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits,
+                               int mode, float* out_scores, int64_t* out_rows);
 /* Deferred form for a stream of independent queries (throughput mode): vs_exchange_begin opens a
  * new exchange; each vs_query_topk_push_dev runs the local query and pushes its candidates into
  * slots [slot0, slot0+B) of every peer (fused into the scan kernel as above, no waiting); ONE

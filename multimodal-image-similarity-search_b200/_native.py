@@ -59,6 +59,7 @@ SYMBOLS = {
     "vs_query_topk_sharded_dev": (_i, [_p, _p, _i, _i, _p, _i, _p, _p, _p]),
     "vs_exchange_merge_dev": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "vs_exchange_error": (_i, [_p]),
+    "vs_query_topk_sharded_host": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),
     "vs_exchange_begin": (_i, [_p]),
     "vs_query_topk_push_dev": (_i, [_p, _p, _i, _i, _p, _i, _i, _p]),
     "vs_exchange_collect_dev": (_i, [_p, _i, _i, _p, _p, _p]),

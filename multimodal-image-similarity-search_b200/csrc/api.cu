@@ -863,6 +863,35 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
   return VS_OK;
 }
 
+int vs_query_topk_sharded_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits, int mode,
+                               float* out_scores, int64_t* out_rows) {
+  if (!ix) return fail(VS_ERR_ARG, "index is NULL");
+  if (B <= 0 || !q || !out_scores || !out_rows) return fail(VS_ERR_ARG, "bad B or NULL buffer");
+  const size_t qbytes = (size_t)B * ix->dim * 4, sbytes = (size_t)B * k * 4, rbytes = (size_t)B * k * 8;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    CU(ix->d_q.reserve(qbytes));
+    CU(ix->d_out_s.reserve(sbytes + rbytes + 64));   // scores | rows in ONE buffer: one D2H
+    CU(ix->h_in.reserve(qbytes));
+    CU(ix->h_out.reserve(sbytes + rbytes + 64));
+    memcpy(ix->h_in.p, q, qbytes);
+    CU(cudaMemcpyAsync(ix->d_q.p, ix->h_in.p, qbytes, cudaMemcpyHostToDevice, ix->stream));
+  }
+  float* d_s = (float*)ix->d_out_s.p;
+  int64_t* d_r = (int64_t*)((char*)ix->d_out_s.p + ((sbytes + 15) & ~(size_t)15));
+  int rc = vs_query_topk_sharded_dev(ix, (const float*)ix->d_q.p, B, k, require_bits, mode, d_s, d_r, nullptr);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  const size_t roff = (sbytes + 15) & ~(size_t)15;
+  CU(cudaMemcpyAsync(ix->h_out.p, ix->d_out_s.p, roff + rbytes, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  memcpy(out_scores, ix->h_out.p, sbytes);
+  memcpy(out_rows, (char*)ix->h_out.p + roff, rbytes);
+  return VS_OK;
+}
+
 int vs_exchange_begin(vs_index_t* ix) {
   if (!ix) return fail(VS_ERR_ARG, "index is NULL");
   std::lock_guard<std::mutex> lk(ix->mu);

@@ -289,6 +289,21 @@ class DeviceIndex:
                                                     _MODES[mode], _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
         return out_scores, out_rows
 
+    def query_sharded(self, q, k: int, require_bits: Optional[Sequence[int]] = None, mode: str = "auto"
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+        """HOST-buffer sharded query (vs_query_topk_sharded_host): H2D, kernel + fused exchange, D2H."""
+        a = np.ascontiguousarray(q, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[None]
+        if a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"expected [B,{self.dim}] queries, got {a.shape}")
+        B = a.shape[0]
+        s = np.empty((B, k), dtype=np.float32)
+        r = np.empty((B, k), dtype=np.int64)
+        N.check(self._lib.vs_query_topk_sharded_host(self._h, a.ctypes.data, B, int(k), _bits_array(require_bits),
+                                                     _MODES[mode], s.ctypes.data, r.ctypes.data))
+        return s, r
+
     def exchange_merge_dev(self, cand_scores, cand_rows, out_scores=None, out_rows=None, stream=None):
         """The exchange kernel alone (vs_exchange_merge_dev): this rank's [B,k] candidates (global
         rows) are pushed into every peer's buffer, flags are exchanged, and the G lists are merged."""

@@ -55,6 +55,10 @@ def main():
         for b, (s, r) in enumerate(outs):
             ok, why = O.topk_matches(s[0].cpu().numpy(), r[0].cpu().numpy(), full[b], 10, tol)
             assert ok, why
+        # host-buffer flavour (one C call per request on every rank)
+        hs, hr = ix.query_sharded(Q[:5], 10, mode="scan")
+        s2, r2 = nccl.search(qd[:5], 10)
+        assert np.array_equal(hr, r2.cpu().numpy()) and np.array_equal(hs, s2.cpu().numpy())
         # throughput mode: 32 pushes, one collect
         s, r = p2p.peer_exchange.search_stream([qd[b:b + 1] for b in range(32)], 10, mode="scan")
         s2, r2 = nccl.search(qd[:32], 10)
