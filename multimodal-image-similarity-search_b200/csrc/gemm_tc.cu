@@ -6,20 +6,26 @@
 //
 // One warp-specialised kernel, three epilogues.  D[m, n] = sum_k A[m, k] * B[n, k] with
 //   A = a block of 128 "query-side" vectors (queries / prompts / a block of corpus rows), bf16,
-//       RESIDENT in shared memory for the whole work item (loaded once by TMA, 128B swizzle),
+//       128B swizzle; RESIDENT in shared memory for the whole work item when that leaves a deep
+//       enough ring (dim <= 512 in pair mode), else its 16 KB k-block travels with every stage,
 //   B = corpus rows, streamed from HBM in tiles of BN rows x 64 k-elements by TMA into a ring of
 //       stages.  The C CTAs of a thread-block CLUSTER own C different A blocks and share ONE
-//       corpus stream: each CTA fetches 1/C of every B tile and TMA-multicasts it into the
-//       shared memory of all C CTAs, so a corpus byte crosses L2->SM once per cluster instead of
-//       once per A block (without this the kernel is L2-bandwidth bound: 64 B/cycle/SM),
+//       corpus stream: each CTA fetches 1/C of every B tile and TMA-multicasts it to the CTAs that
+//       need it, so a corpus byte crosses L2->SM once per cluster instead of once per A block,
 //   D = fp32 accumulators in TMEM: lane = query, column = corpus row, 512/BN buffers so the MMA
 //       of tile t+1 overlaps the epilogue of tile t.
-// Roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread), warps 2..9 =
-// epilogue (tcgen05.ld 32x32b: each thread owns ONE query and sees that query's scores against
-// 32 consecutive rows per load -> a private register top-k list, no cross-thread traffic).
+// Issue mode (template CG): CG = 2 (default) pairs the CTAs (2p, 2p+1) of the cluster with
+// tcgen05 cta_group::2 -- the even CTA issues one M = 256 MMA for both A blocks and each CTA holds
+// only its half of the B tile; CG = 1 issues M = 128 MMAs per CTA.
+// Roles: warp 0 = TMA producer (rows, A k-blocks, the tile's inverse norms and group bounds),
+// warp 1 = tcgen05.mma issuer (one elected thread), warps 2..9 = epilogue (tcgen05.ld 32x32b: each
+// thread owns ONE query and sees that query's scores against 32 consecutive rows per load -> a
+// private register top-k list, no cross-thread traffic).
 // Epilogue arithmetic: score = acc * inv_norm[row] (queries are L2-normalised then rounded to
-// bf16 by prep_queries_kernel; the oracle does the same), filter bits are only fetched for rows
-// that would enter a list, nothing but the final candidates is written.
+// bf16 by prep_queries_kernel; the oracle does the same); a fast reject on the raw accumulators
+// against a per-query bound shared by all lists (pool of k class maxima) keeps the exact path rare;
+// filter bits are only fetched for rows that would enter a list, nothing but the final candidates
+// is written.
 #include <cuda.h>
 
 #include <cstdlib>
