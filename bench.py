@@ -77,8 +77,15 @@ def measured_peaks():
 def cpu_reference_qps(total_rows: int, dim: int, k: int, budget_s: float, sample_rows: int = 1_000_000,
                       min_queries: int = 3):
     from oracle import cosine_oracle as O
-    import torch
-    threads = torch.get_num_threads()
+    # all the host threads BLAS can use, also under torchrun (which exports OMP_NUM_THREADS=1)
+    ncores = int(os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        _limit = threadpool_limits(limits=ncores)
+        threads = max([d.get("num_threads", 1) for d in threadpool_info()] or [1])
+    except Exception:                                 # noqa: BLE001
+        import torch
+        _limit, threads = None, torch.get_num_threads()
     rng = np.random.default_rng(0)
     sample_rows = min(sample_rows, total_rows)
     X = O.bf16_round(O.normalize_rows(rng.standard_normal((sample_rows, dim), dtype=np.float32)))
@@ -100,6 +107,8 @@ def cpu_reference_qps(total_rows: int, dim: int, k: int, budget_s: float, sample
         if (dt >= budget_s and n >= min_queries) or n >= 4096:
             break
     qps_sample = n / dt
+    if _limit is not None:
+        _limit.restore_original_limits()
     return {
         "value": qps_sample * sample_rows / total_rows,
         "unit": "queries/s",
