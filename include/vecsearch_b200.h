@@ -13,9 +13,15 @@
  *  - plain C: pointers + sizes, int status return (0 = ok, <0 = error, text via
  *    vs_last_error()); no exceptions, no torch types, no hidden allocation on the query path
  *    beyond per-index scratch that is grown once and reused.
- *  - one vs_index_t == one row shard resident in the HBM of ONE device.  Multi-GPU = one
- *    process per GPU, each owning a shard; candidates are exchanged by the host layer
- *    (NCCL all-gather) and merged with vs_merge_topk_dev.
+ *  - one vs_index_t == one row shard resident in the HBM of ONE device.  Multi-GPU = either ONE
+ *    process holding a vs_group_t (one shard per GPU, worker thread per GPU, the reference's
+ *    single-server shape) or one process per GPU, each owning a shard; either way the candidates
+ *    are exchanged over NVLink peer memory from inside the query kernel (vs_exchange_*), or by
+ *    the host layer (NCCL all-gather) and merged with vs_merge_topk_dev.
+ *  - thread safety: every entry point locks the handle for its whole body, so concurrent callers
+ *    on one handle serialise (staging buffers are per handle); different handles are independent.
+ *    "_dev" entry points return when the work is enqueued; mutations (add / remove / set_row /
+ *    filter bits) order themselves after queries still in flight on caller streams.
  *  - "_host" entry points take HOST buffers and include the H2D/D2H copies and the final
  *    stream synchronise; "_dev" entry points take DEVICE buffers and are asynchronous on the
  *    given cudaStream_t (passed as void*; NULL = the index's own stream).
@@ -44,7 +50,8 @@ enum {
   VS_ERR_CUDA = -2,   /* CUDA runtime / driver error, or no usable device */
   VS_ERR_OOM = -3,    /* device allocation failed */
   VS_ERR_UNSUPPORTED = -4,
-  VS_ERR_OVERFLOW = -5 /* caller-provided output buffer too small (dedup pairs) */
+  VS_ERR_OVERFLOW = -5, /* caller-provided output buffer too small (dedup pairs) */
+  VS_ERR_EXCHANGE = -6  /* a peer shard never delivered its candidates: the affected results are EMPTY, not stale */
 };
 
 /* number of filter bits carried per row (4 x u64) -- the reference UI never has more than a
@@ -67,6 +74,9 @@ int vs_destroy(vs_index_t* ix);
 int64_t vs_count(const vs_index_t* ix);
 int vs_dim(const vs_index_t* ix);
 int vs_dtype(const vs_index_t* ix);
+int vs_device(const vs_index_t* ix);
+/* Grow the slab to hold at least capacity_rows rows now (bulk loads: no re-allocation later). */
+int vs_reserve(vs_index_t* ix, int64_t capacity_rows);
 
 /* Offset added to every row number this shard reports (global row = row_base + local row). */
 int vs_set_row_base(vs_index_t* ix, int64_t row_base);
@@ -81,10 +91,38 @@ int vs_set_row_map(vs_index_t* ix, int64_t row_base, int64_t row_stride);
 int vs_add_host(vs_index_t* ix, const float* rows, int64_t n, int64_t* first_row);
 int vs_add_dev(vs_index_t* ix, const float* rows_dev, int64_t n, int64_t* first_row, void* stream);
 
+/* Persistence slab (the store the reference reopens at backend/app/utils.py:109-123 and
+ * walks at backend/app/main.py:522-579): rows in the STORAGE dtype (bf16 / f32), dim elements each,
+ * no pitch padding.  vs_get_raw_host copies stored rows out bit for bit; vs_add_raw_host appends such
+ * rows through double-buffered pinned staging and recomputes the inverse norms on the device, so a
+ * reloaded collection scores bit-identically to the saved one. */
+int vs_add_raw_host(vs_index_t* ix, const void* stored_rows, int64_t n, int64_t* first_row);
+int vs_get_raw_host(const vs_index_t* ix, int64_t first_row, int64_t n, void* out);
+
 /* ---- Collection.delete(ids)  (backend/app/main.py:1069).  Removes local row `row` by moving
  *      the LAST row into its place (dense slab, no tombstones).  *moved_from = the row that was
  *      moved (== old count-1), or -1 if `row` was the last row. */
 int vs_remove(vs_index_t* ix, int64_t row, int64_t* moved_from);
+/* Bulk form (reset_system deletes every id in one call, backend/app/main.py:1065-1069): removes the m
+ * distinct rows `rows[]` with ONE compaction kernel and one synchronise.  The new count is count - m;
+ * every hole below it is filled by a surviving row from at or above it.  The moves are reported as
+ * moved_src[i] -> moved_dst[i], i < *n_moved <= m (both arrays must hold m entries) so the host layer
+ * can re-point its id<->row map. */
+int vs_remove_rows(vs_index_t* ix, const int64_t* rows, int64_t m, int64_t* moved_src, int64_t* moved_dst,
+                   int64_t* n_moved);
+/* Drop the rows at and above new_count (keeps the allocation). */
+int vs_truncate(vs_index_t* ix, int64_t new_count);
+/* dst row <- src row (vector, inverse norm, filter bits), possibly across two GPUs of this process
+ * (a group's delete moves the LAST global row into the hole, which may live on another shard). */
+int vs_copy_row(vs_index_t* dst, int64_t dst_row, vs_index_t* src, int64_t src_row);
+/* Batched form: dst row dst_rows[i] <- src row src_rows[i], i < n, in ONE kernel on dst's GPU (the source
+ * shard is read over NVLink peer memory).  Sources and destinations must be disjoint rows when dst == src.
+ * A group's bulk delete issues at most G*G of these and then vs_truncate()s every shard. */
+int vs_move_rows(vs_index_t* dst, vs_index_t* src, const int64_t* src_rows, const int64_t* dst_rows, int64_t n);
+/* dst row (dst_first + l * dst_stride) <- src row l for every row of src (vectors + inverse norms), read
+ * over NVLink peer memory by a kernel on dst's GPU; dst grows as needed.  Replicates the row-striped
+ * shards of a group into one full index per GPU for the all-pairs pass. */
+int vs_replicate_from(vs_index_t* dst, vs_index_t* src, int64_t dst_first, int64_t dst_stride);
 
 /* Overwrite the vector of an existing row in place (the row-striped sharded collection moves the
  * LAST global row into a deleted row's slot, which may live on another shard). */
@@ -99,6 +137,11 @@ int vs_set_mask_bits(vs_index_t* ix, int64_t row, const uint64_t bits[VS_MASK_WO
 int vs_get_mask_bits(const vs_index_t* ix, int64_t row, uint64_t bits[VS_MASK_WORDS]);
 /* Bulk form for ingest: bits[n][VS_MASK_WORDS] for rows [first_row, first_row + n) in ONE copy. */
 int vs_set_mask_bits_range(vs_index_t* ix, int64_t first_row, int64_t n, const uint64_t* bits);
+int vs_get_mask_bits_range(const vs_index_t* ix, int64_t first_row, int64_t n, uint64_t* bits);
+/* Filter sweep -> stored bits without leaving the GPU: filter bit `bit` of every row r := bit r of
+ * words_dev (one filter's row of vs_filter_sweep_dev output).  The CLIP-side analogue of the answers
+ * the Moondream loop writes at backend/app/main.py:1010-1033. */
+int vs_apply_sweep_bits_dev(vs_index_t* ix, const uint32_t* words_dev, int bit, void* stream);
 
 /* Copy stored rows back as float32 (Collection.get(include=["embeddings"]) and persistence). */
 int vs_get_rows_host(const vs_index_t* ix, int64_t first_row, int64_t n, float* out);
@@ -112,8 +155,14 @@ int vs_get_rows_dev(const vs_index_t* ix, int64_t first_row, int64_t n, float* o
  *      filter bits contain all required bits compete ("pre" filter mode, fused in the scan).
  *      mode: VS_Q_AUTO picks the HBM-bound scan (B small, or f32 storage) or the tcgen05
  *      batched kernel (bf16 storage, B >= 16); the other values force one path.
- *      out_scores/out_rows: [B, k].  k <= 1024 (main.py:757 caps "All" at 1000). */
-enum { VS_Q_AUTO = 0, VS_Q_SCAN = 1, VS_Q_TENSOR = 2 };
+ *      out_scores/out_rows: [B, k].  k <= 1024 (main.py:757 caps "All" at 1000).
+ *      VS_Q_PIPELINED may be OR-ed into `mode` of a "_dev" call: the caller vouches that the query
+ *      buffer was complete BEFORE the previous vecsearch launch on that stream (e.g. a batch of
+ *      queries prepared up front and issued one call each).  The scan kernel then starts streaming
+ *      while the previous query still merges (programmatic dependent launch with the
+ *      griddepcontrol.wait deferred past the scan).  Without it -- the default -- the kernel waits
+ *      for everything before it in the stream before reading q or any row. */
+enum { VS_Q_AUTO = 0, VS_Q_SCAN = 1, VS_Q_TENSOR = 2, VS_Q_PIPELINED = 0x100 };
 int vs_query_topk_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits,
                        int mode, float* out_scores, int64_t* out_rows);
 int vs_query_topk_dev(vs_index_t* ix, const float* q_dev, int B, int k, const uint64_t* require_bits,
@@ -154,7 +203,10 @@ int vs_merge_topk_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_
  *      local query and one exchange kernel with the same wire protocol.  All ranks must issue the
  *      same sequence of sharded queries (same B, k); k <= k_max <= 128; global rows < 2^32.
  *      vs_exchange_merge_dev exposes the exchange kernel alone for caller-made [B,k] candidates.
- *      vs_exchange_error() != 0 (after a synchronise) means a peer never arrived: results invalid. */
+ *      A wait that times out (~3 s: a peer never pushed) NEVER merges stale lists: the affected
+ *      results are written EMPTY (-inf, -1) and a sticky error word in host-mapped memory is raised.
+ *      vs_exchange_error() reads it (no CUDA call); the "_host" entry points return VS_ERR_EXCHANGE and
+ *      re-arm; "_dev" entry points refuse further exchanges until vs_exchange_clear_error(). */
 size_t vs_exchange_bytes(int B_max, int k_max, int G);
 int vs_exchange_create(vs_index_t* ix, int G, int rank, int B_max, int k_max);
 int vs_exchange_ipc_handle(vs_index_t* ix, unsigned char handle_out[64]);
@@ -165,6 +217,7 @@ int vs_query_topk_sharded_dev(vs_index_t* ix, const float* q_dev, int B, int k, 
 int vs_exchange_merge_dev(vs_index_t* ix, const float* cand_scores_dev, const int64_t* cand_rows_dev, int B,
                           int k, float* out_scores_dev, int64_t* out_rows_dev, void* stream);
 int vs_exchange_error(vs_index_t* ix);
+int vs_exchange_clear_error(vs_index_t* ix);
 /* HOST-buffer flavour of vs_query_topk_sharded_dev (one call per request on every rank: pinned H2D of
  * the replicated queries, query kernel with the fused exchange, D2H of the global result, sync). */
 int vs_query_topk_sharded_host(vs_index_t* ix, const float* q, int B, int k, const uint64_t* require_bits,
@@ -179,6 +232,32 @@ int vs_query_topk_push_dev(vs_index_t* ix, const float* q_dev, int B, int k, con
                            int mode, int slot0, void* stream);
 int vs_exchange_collect_dev(vs_index_t* ix, int B, int k, float* out_scores_dev, int64_t* out_rows_dev,
                             void* stream);
+
+/* ---- vs_group_t: the reference's deployment shape -- ONE server process (backend/run.py:10-14) -- on all
+ *      GPUs of the box.  n_dev row shards (global row g lives on shard g % n_dev at local row g / n_dev;
+ *      every kernel reports global rows), their exchange buffers wired by pointer, and one resident worker
+ *      thread per GPU.  vs_group_query_host is the request/response path of search_similar
+ *      (backend/app/main.py:748-805): the query is written into a pinned host-mapped area, every worker
+ *      issues one small H2D + ONE fused scan launch on its GPU, the kernels exchange candidates over NVLink
+ *      and shard 0's kernel writes the global [B, k] result and a completion flag straight into host-mapped
+ *      memory, which the calling thread polls -- no stream synchronise, no result copy, no torchrun.
+ *      B > 64 / the tcgen05 path / k > k_max (gathered onto GPU 0 over NVLink and merged there) use the
+ *      same entry point.  Ingest and maintenance go through the shards: vs_group_shard(g, s) returns the
+ *      vs_index_t of shard s (row map (s, n_dev) already set).  devices == NULL means 0..n_dev-1. */
+typedef struct vs_group vs_group_t;
+int vs_group_create(int n_dev, const int* devices, int dim, int dtype, int64_t capacity_rows_total, int b_max,
+                    int k_max, vs_group_t** out);
+int vs_group_destroy(vs_group_t* g);
+int vs_group_size(const vs_group_t* g);
+vs_index_t* vs_group_shard(vs_group_t* g, int shard);
+int64_t vs_group_count(const vs_group_t* g);
+int vs_group_query_host(vs_group_t* g, const float* q, int B, int k, const uint64_t* require_bits, int mode,
+                        float* out_scores, int64_t* out_rows);
+/* search_multimodal (backend/app/main.py:829-867) on a group: every GPU blends its own copy of the
+ * (img, txt, w) triples (vs_blend_dev's kernel), then the same query path. */
+int vs_group_query_multimodal_host(vs_group_t* g, const float* img, const float* txt, const double* w, int B,
+                                   int k, const uint64_t* require_bits, int mode, float* out_scores,
+                                   int64_t* out_rows);
 
 /* ---- filter sweep (BASELINE config 4; CLIP-side analogue of process_filter_on_all_images,
  *      backend/app/main.py:939-1056): prompts [F, dim] float32 (host or device) -> bit mask

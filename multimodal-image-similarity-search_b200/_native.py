@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("VS_LIB_PATH") or os.path.join(_HERE, LIB_NAME)
 VS_F32, VS_BF16 = 0, 1
 VS_Q_AUTO, VS_Q_SCAN, VS_Q_TENSOR = 0, 1, 2
 VS_ERR_OVERFLOW = -5
+VS_ERR_EXCHANGE = -6
+VS_Q_PIPELINED = 0x100
 MASK_WORDS = 4
 MAX_K = 1024
 
@@ -34,6 +36,25 @@ SYMBOLS = {
     "vs_count": (_i64, [_p]),
     "vs_dim": (_i, [_p]),
     "vs_dtype": (_i, [_p]),
+    "vs_device": (_i, [_p]),
+    "vs_reserve": (_i, [_p, _i64]),
+    "vs_add_raw_host": (_i, [_p, _p, _i64, C.POINTER(_i64)]),
+    "vs_get_raw_host": (_i, [_p, _i64, _i64, _p]),
+    "vs_remove_rows": (_i, [_p, _p, _i64, _p, _p, C.POINTER(_i64)]),
+    "vs_truncate": (_i, [_p, _i64]),
+    "vs_copy_row": (_i, [_p, _i64, _p, _i64]),
+    "vs_move_rows": (_i, [_p, _p, _p, _p, _i64]),
+    "vs_replicate_from": (_i, [_p, _p, _i64, _i64]),
+    "vs_get_mask_bits_range": (_i, [_p, _i64, _i64, _p]),
+    "vs_apply_sweep_bits_dev": (_i, [_p, _p, _i, _p]),
+    "vs_exchange_clear_error": (_i, [_p]),
+    "vs_group_create": (_i, [_i, _p, _i, _i, _i64, _i, _i, C.POINTER(_p)]),
+    "vs_group_destroy": (_i, [_p]),
+    "vs_group_size": (_i, [_p]),
+    "vs_group_shard": (_p, [_p, _i]),
+    "vs_group_count": (_i64, [_p]),
+    "vs_group_query_host": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),
+    "vs_group_query_multimodal_host": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p]),
     "vs_set_row_base": (_i, [_p, _i64]),
     "vs_set_row_map": (_i, [_p, _i64, _i64]),
     "vs_add_host": (_i, [_p, _p, _i64, C.POINTER(_i64)]),

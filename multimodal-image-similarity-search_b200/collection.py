@@ -15,10 +15,26 @@ by the sm_100a kernels behind ``libvecsearch_b200.so``.  Exact search: there is 
 so recall is 1 by construction.
 
 Host-side state (ids, metadata dicts, documents) lives in Python, as it lives in SQLite inside
-chromadb; vectors, inverse norms and filter bits live in HBM.
+chromadb; vectors, inverse norms and filter bits live in HBM.  The backing index is a
+``DeviceIndex`` (one GPU), a ``GroupIndex`` (one process, all GPUs of the box) or a ``ShardedIndex``
+(one process per GPU); the collection only uses their common surface.
+
+Persistence (``path=``; the directory the reference reopens at ``utils.py:109-123`` and walks at
+``main.py:522-579``) is a SNAPSHOT + OPERATION LOG:
+
+* snapshot of generation g -- ``rows.<g>.bin`` (raw row slab in the storage dtype, bf16 or f32),
+  ``ids.<g>.txt``, ``meta.<g>.jsonl``, ``docs.<g>.jsonl``, ``masks.<g>.u64`` (filter bits) -- is loaded by
+  chunked pinned host->device copies (``vs_add_raw_host``; a GroupIndex stripes it over its GPUs);
+  metadata lines stay unparsed until somebody reads them;
+* ``oplog.<g>.jsonl`` + ``oplog.<g>.vec`` hold what happened since: every record carries the byte offset of
+  its vectors, a torn tail is ignored and truncated, the files are flushed as one unit per call;
+* a checkpoint (``persist()``, ``close()``, or automatically when the log outgrows the snapshot) writes
+  generation g+1, switches ``collection.json`` atomically, and drops the old files -- deleted rows vanish
+  from disk at that point (compaction).
 """
 from __future__ import annotations
 
+import base64
 import json
 import os
 import threading
@@ -31,6 +47,7 @@ from .index import DeviceIndex
 _SCALAR = (str, int, float, bool)
 FILTER_JSON_KEY = "filter_results_json"   # reference: backend/app/main.py:731, 1024
 MAX_FILTERS = 256
+FORMAT_VERSION = 2
 
 
 def _is_cuda_rows(x) -> bool:
@@ -63,26 +80,39 @@ def _as_rows(embeddings, dim: Optional[int]) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
-class _NoRows:
-    """Placeholder for device rows that need no host copy (in-memory collection: nothing is logged)."""
-
-    def __init__(self, dim: int):
-        self.shape = (0, dim)
-
-    def __getitem__(self, j):
-        return None
-
-
 def _yes(answer: Any) -> bool:
     """The predicate of backend/app/main.py:215."""
     return isinstance(answer, str) and answer.lower().strip() == "yes"
+
+
+def _answers_of(meta: Optional[Dict[str, Any]]) -> Dict[str, Any]:
+    """``json.loads(meta["filter_results_json"])`` with the reference's failure mode (main.py:207-213): {}."""
+    if not meta or FILTER_JSON_KEY not in meta:
+        return {}
+    try:
+        answers = json.loads(meta[FILTER_JSON_KEY])
+    except (json.JSONDecodeError, TypeError):
+        return {}
+    return answers if isinstance(answers, dict) else {}
+
+
+def _fsync_dir(path: str):
+    try:
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            os.fsync(fd)
+        finally:
+            os.close(fd)
+    except OSError:
+        pass
 
 
 class Collection:
     """Duck-type of ``chromadb.api.models.Collection`` restricted to what the reference calls."""
 
     def __init__(self, name: str, metadata: Optional[Dict[str, Any]] = None, *, device: int = 0,
-                 dtype: str = "f32", path: Optional[str] = None, row_base: int = 0, index=None):
+                 dtype: str = "f32", path: Optional[str] = None, row_base: int = 0, index=None,
+                 index_factory=None, durable: bool = False):
         metadata = dict(metadata or {})
         space = metadata.get("hnsw:space", "cosine")
         if space != "cosine":
@@ -90,18 +120,27 @@ class Collection:
         self.name = name
         self.metadata = metadata
         self._device, self._dtype, self._row_base = device, dtype, row_base
-        # created on first add (dimension fixed then), or injected: a ShardedIndex spanning several GPUs
-        self._index: Optional[DeviceIndex] = index
+        # created on first add (dimension fixed then) by index_factory(dim) / DeviceIndex, or injected
+        self._index = index
+        self._index_factory = index_factory
         self._ids: List[str] = []
         self._row_of: Dict[str, int] = {}
-        self._metas: List[Optional[Dict[str, Any]]] = []
-        self._docs: List[Optional[str]] = []
+        # metadata / document of row r; a ``bytes`` entry is a raw JSON line of the snapshot, parsed on first use
+        self._metas: List[Any] = []
+        self._docs: List[Any] = []
         self._filters: List[str] = []                 # filter name -> bit index
+        self._swept: set = set()                      # filters whose answers live in the device bits (apply_filter_sweep)
+        self.filter_progress: Dict[str, Dict[str, Any]] = {}   # shape of main.py:964-986, served by /api/filter-progress
         self._lock = threading.RLock()                # update() runs on a worker thread (main.py:410)
         self._path = path
-        self._log = None
+        self._durable = durable
+        self._gen = 0
+        self._log = self._vec = None
+        self._log_ops = 0
+        self._log_rows = 0
+        self._snap_rows = 0
         if path is not None:
-            self._open_log()
+            self._open_store()
 
     # ------------------------------------------------------------------ internals
     @property
@@ -109,12 +148,15 @@ class Collection:
         return None if self._index is None else self._index.dim
 
     @property
-    def index(self) -> Optional[DeviceIndex]:
+    def index(self):
         return self._index
 
-    def _ensure_index(self, dim: int) -> DeviceIndex:
+    def _ensure_index(self, dim: int):
         if self._index is None:
-            self._index = DeviceIndex(dim, self._dtype, self._device, row_base=self._row_base)
+            if self._index_factory is not None:
+                self._index = self._index_factory(dim)
+            else:
+                self._index = DeviceIndex(dim, self._dtype, self._device, row_base=self._row_base)
         return self._index
 
     def _filter_bit(self, name: str, create: bool) -> Optional[int]:
@@ -128,25 +170,57 @@ class Collection:
             self._filters.append(name)
             return len(self._filters) - 1
 
-    def _sync_filter_bits(self, row: int):
-        """Mirror the row's ``filter_results_json`` "yes" answers into its device filter bits."""
-        self._index.set_filter_bits(row, self._filter_bits_of(row))
+    def _meta(self, row: int) -> Optional[Dict[str, Any]]:
+        m = self._metas[row]
+        if isinstance(m, bytes):
+            m = json.loads(m) if m and m != b"null" else None
+            self._metas[row] = m
+        return m
 
-    def _filter_bits_of(self, row: int) -> List[int]:
-        meta = self._metas[row] or {}
-        bits = []
-        raw = meta.get(FILTER_JSON_KEY)
-        if raw is not None:
-            try:
-                answers = json.loads(raw)
-            except (json.JSONDecodeError, TypeError):
-                answers = {}
-            if isinstance(answers, dict):
-                for fname, ans in answers.items():
-                    b = self._filter_bit(fname, create=True)
-                    if _yes(ans):
-                        bits.append(b)
-        return bits
+    def _doc(self, row: int) -> Optional[str]:
+        d = self._docs[row]
+        if isinstance(d, bytes):
+            d = json.loads(d) if d and d != b"null" else None
+            self._docs[row] = d
+        return d
+
+    def _swept_answers(self, row: int) -> Dict[str, str]:
+        """Answers of swept filters for one row, read from its device bits."""
+        if not self._swept:
+            return {}
+        have = set(self._index.get_filter_bits(row))
+        return {f: ("yes" if self._filters.index(f) in have else "no") for f in self._filters if f in self._swept}
+
+    def _meta_out(self, row: int) -> Optional[Dict[str, Any]]:
+        """The metadata a caller sees: stored dict + (lazily) the answers of swept filters merged into
+        ``filter_results_json``, so the reference's post-filter and UI keep working unchanged."""
+        m = self._meta(row)
+        if not self._swept:
+            return dict(m) if m is not None else None
+        out = dict(m or {})
+        answers = _answers_of(m)
+        answers.update(self._swept_answers(row))
+        out[FILTER_JSON_KEY] = json.dumps(answers)
+        return out
+
+    def _json_bits_of(self, meta: Optional[Dict[str, Any]]):
+        """(bits set by "yes" answers, bits mentioned at all) of a row's stored filter_results_json."""
+        yes, named = [], []
+        for fname, ans in _answers_of(meta).items():
+            b = self._filter_bit(fname, create=True)
+            named.append(b)
+            if _yes(ans):
+                yes.append(b)
+        return yes, named
+
+    def _sync_filter_bits(self, row: int):
+        """Mirror the row's ``filter_results_json`` "yes" answers into its device filter bits; bits of swept
+        filters the JSON does not mention are kept."""
+        yes, named = self._json_bits_of(self._meta(row))
+        if self._swept:
+            keep = {self._filters.index(f) for f in self._swept} - set(named)
+            yes = sorted(set(yes) | (set(self._index.get_filter_bits(row)) & keep))
+        self._index.set_filter_bits(row, yes)
 
     @staticmethod
     def _check_meta(m: Optional[Dict[str, Any]]):
@@ -158,52 +232,212 @@ class Collection:
             if not isinstance(k, str) or not isinstance(v, _SCALAR):
                 raise ValueError(f"metadata values must be str, int, float or bool (key {k!r})")
 
-    # ------------------------------------------------------------------ persistence (append-only log)
-    def _open_log(self):
+    # ------------------------------------------------------------------ persistence: snapshot + operation log
+    def _f(self, stem: str, gen: Optional[int] = None) -> str:
+        g = self._gen if gen is None else gen
+        base, ext = stem.split(".")
+        return os.path.join(self._path, f"{base}.{g}.{ext}")
+
+    def _manifest_path(self) -> str:
+        return os.path.join(self._path, "collection.json")
+
+    def _read_manifest(self) -> Dict[str, Any]:
+        try:
+            with open(self._manifest_path(), "r", encoding="utf-8") as f:
+                return json.load(f)
+        except FileNotFoundError:
+            return {}
+
+    def _write_manifest(self, **extra):
+        info = self._read_manifest()
+        info.update({"name": self.name, "metadata": self.metadata, "dtype": self._dtype, "format": FORMAT_VERSION})
+        info.update(extra)
+        tmp = self._manifest_path() + ".tmp"
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(info, f)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, self._manifest_path())
+        _fsync_dir(self._path)
+
+    def _open_store(self):
         os.makedirs(self._path, exist_ok=True)
-        log = os.path.join(self._path, "oplog.jsonl")
-        vec = os.path.join(self._path, "vectors.f32")
-        if os.path.exists(log):
-            self._replay(log, vec)
-        self._log = open(log, "a", encoding="utf-8")
-        self._vec = open(vec, "ab")
+        info = self._read_manifest()
+        if info.get("format", FORMAT_VERSION) != FORMAT_VERSION and "gen" in info:
+            raise ValueError(f"{self._path}: unknown collection format {info.get('format')}")
+        self._gen = int(info.get("gen", 0))
+        if info.get("count", 0) > 0:
+            self._load_snapshot(info)
+        self._replay_log()
+        self._log = open(self._f("oplog.jsonl"), "ab")
+        self._vec = open(self._f("oplog.vec"), "ab")
+        # stale generations (a crash between the manifest switch and the clean-up)
+        for fn in os.listdir(self._path):
+            parts = fn.split(".")
+            if len(parts) == 3 and parts[1].isdigit() and int(parts[1]) != self._gen and \
+                    parts[0] in ("rows", "ids", "meta", "docs", "masks", "oplog"):
+                try:
+                    os.remove(os.path.join(self._path, fn))
+                except OSError:
+                    pass
 
-    def _replay(self, log: str, vec: str):
-        with open(log, "r", encoding="utf-8") as f, open(vec, "rb") as v:
-            pend_ids, pend_rows, pend_meta, pend_doc = [], [], [], []
+    def _load_snapshot(self, info: Dict[str, Any]):
+        n, dim = int(info["count"]), int(info["dim"])
+        self._filters = list(info.get("filters", []))
+        self._swept = set(info.get("swept", []))
+        ix = self._ensure_index(dim)
+        if hasattr(ix, "reserve"):
+            ix.reserve(n)
+        if hasattr(ix, "add_raw"):
+            slab = np.memmap(self._f("rows.bin"), dtype=ix.storage_dtype, mode="r", shape=(n, dim))
+            ix.add_raw(slab)                            # chunked pinned host -> device, per GPU of a group
+            del slab
+        else:                                           # an index without the raw path (tests' fake): f32 rows
+            ix.add(np.fromfile(self._f("rows.bin"), dtype=np.float32).reshape(n, dim))
+        with open(self._f("ids.txt"), "rb") as f:
+            raw = f.read()
+        if info.get("ids_format") == "json":
+            self._ids = [json.loads(line) for line in raw.split(b"\n")[:n]]
+        else:
+            self._ids = raw.decode("utf-8").split("\n")[:n]
+        if len(self._ids) != n:
+            raise ValueError(f"{self._path}: snapshot holds {len(self._ids)} ids for {n} rows")
+        self._row_of = dict(zip(self._ids, range(n)))
+        with open(self._f("meta.jsonl"), "rb") as f:
+            self._metas = f.read().split(b"\n")[:n]     # parsed lazily (_meta)
+        with open(self._f("docs.jsonl"), "rb") as f:
+            self._docs = f.read().split(b"\n")[:n]
+        if len(self._metas) != n or len(self._docs) != n:
+            raise ValueError(f"{self._path}: snapshot metadata/documents do not match {n} rows")
+        mp = self._f("masks.u64")
+        if os.path.exists(mp):
+            words = np.fromfile(mp, dtype=np.uint64).reshape(n, -1)
+            if hasattr(ix, "set_filter_words_range"):
+                ix.set_filter_words_range(0, words)
+            else:
+                ix.set_filter_bits_range(0, [[b for b in range(64 * words.shape[1]) if (int(w[b // 64]) >> (b % 64)) & 1]
+                                             for w in words])
+        self._snap_rows = n
 
-            def flush():
-                if pend_ids:
-                    self._add_rows(pend_ids, np.stack(pend_rows), pend_meta, pend_doc, log=False)
-                    pend_ids.clear(); pend_rows.clear(); pend_meta.clear(); pend_doc.clear()
-
+    def _replay_log(self):
+        log, vec = self._f("oplog.jsonl"), self._f("oplog.vec")
+        if not os.path.exists(log):
+            return
+        good_log = good_vec = 0
+        with open(log, "rb") as f, open(vec, "rb") if os.path.exists(vec) else open(os.devnull, "rb") as v:
+            vec_size = os.path.getsize(vec) if os.path.exists(vec) else 0
             for line in f:
-                op = json.loads(line)
-                if op["op"] == "add":
-                    row = np.frombuffer(v.read(4 * op["dim"]), dtype=np.float32)
-                    pend_ids.append(op["id"]); pend_rows.append(row)
-                    pend_meta.append(op.get("metadata")); pend_doc.append(op.get("document"))
-                    if len(pend_ids) >= 65536:
-                        flush()
-                else:
-                    flush()
-                    if op["op"] == "update":
-                        self._update_one(op["id"], op.get("metadata"), op.get("document"), log=False)
-                    elif op["op"] == "delete":
-                        self._delete_ids([op["id"]], log=False)
-            flush()
+                if not line.endswith(b"\n"):
+                    break                               # torn tail: the record was never completed
+                try:
+                    op = json.loads(line)
+                except json.JSONDecodeError:
+                    break
+                kind = op.get("op")
+                if kind == "add":
+                    nbytes = int(op["nbytes"])
+                    if op["off"] + nbytes > vec_size:
+                        break                           # vectors of this record never reached the disk
+                    v.seek(op["off"])
+                    dt = np.dtype(op["vdtype"])
+                    rows = np.frombuffer(v.read(nbytes), dtype=dt).reshape(len(op["ids"]), op["dim"])
+                    self._add_rows(op["ids"], rows, op.get("metadatas") or [None] * len(op["ids"]),
+                                   op.get("documents") or [None] * len(op["ids"]), log=False, raw=(op["vdtype"] != "float32"))
+                    good_vec = max(good_vec, op["off"] + nbytes)
+                elif kind == "update":
+                    self._update_one(op["id"], op.get("metadata"), op.get("document"), log=False)
+                elif kind == "delete":
+                    self._delete_ids(op["ids"], log=False)
+                elif kind == "sweep":
+                    self._replay_sweep(op)
+                good_log = f.tell()
+                self._log_ops += 1
+        # drop a torn tail / orphan vectors so the next append starts at a clean boundary
+        if good_log != os.path.getsize(log):
+            with open(log, "r+b") as f:
+                f.truncate(good_log)
+        if os.path.exists(vec) and good_vec != os.path.getsize(vec):
+            with open(vec, "r+b") as f:
+                f.truncate(good_vec)
 
-    def _log_op(self, op: Dict[str, Any], row: Optional[np.ndarray] = None):
+    def _log_op(self, op: Dict[str, Any], rows: Optional[np.ndarray] = None):
         if self._log is None:
             return
-        if row is not None:
-            self._vec.write(np.ascontiguousarray(row, dtype=np.float32).tobytes())
-        self._log.write(json.dumps(op, separators=(",", ":")) + "\n")
+        if rows is not None:
+            a = np.ascontiguousarray(rows)
+            op = dict(op, off=self._vec.tell(), nbytes=int(a.nbytes), vdtype=str(a.dtype), dim=int(a.shape[1]))
+            self._vec.write(a.tobytes())
+            self._log_rows += int(a.shape[0])
+        self._log.write(json.dumps(op, separators=(",", ":")).encode("utf-8") + b"\n")
+        self._log_ops += 1
 
     def _log_flush(self):
-        if self._log is not None:
-            self._vec.flush()
-            self._log.flush()
+        """Make the call durable as ONE unit: vectors first, then the records that point at them."""
+        if self._log is None:
+            return
+        self._vec.flush()
+        if self._durable:
+            os.fsync(self._vec.fileno())
+        self._log.flush()
+        if self._durable:
+            os.fsync(self._log.fileno())
+        # the log is replayed op by op on reopen: fold it into a snapshot once it outgrows the snapshot
+        if self._log_ops > 1000 and (self._log_ops + self._log_rows) > max(self._snap_rows, 1) // 2 + 1000:
+            self.persist()
+
+    def persist(self):
+        """Checkpoint: write generation g+1 (compacted -- deleted rows are gone), switch the manifest
+        atomically, drop generation g and its log."""
+        with self._lock:
+            if self._path is None:
+                return
+            n = len(self._ids)
+            old, new = self._gen, self._gen + 1
+            extra: Dict[str, Any] = {"gen": new, "count": n, "filters": list(self._filters), "swept": sorted(self._swept)}
+            if n > 0:
+                ix = self._index
+                extra["dim"] = int(ix.dim)
+                with open(self._f("rows.bin", new), "wb") as f:
+                    step = max(1, (256 << 20) // (ix.dim * 4))
+                    for r0 in range(0, n, step):
+                        m = min(step, n - r0)
+                        rows = ix.get_raw(r0, m) if hasattr(ix, "get_raw") else ix.get_rows(r0, m)
+                        f.write(np.ascontiguousarray(rows).tobytes())
+                    f.flush()
+                    os.fsync(f.fileno())
+                plain = not any("\n" in i for i in self._ids)
+                extra["ids_format"] = "plain" if plain else "json"
+                with open(self._f("ids.txt", new), "wb") as f:
+                    f.write(("\n".join(self._ids) if plain else "\n".join(json.dumps(i) for i in self._ids)).encode("utf-8"))
+                    f.write(b"\n")
+                for stem, items in (("meta.jsonl", self._metas), ("docs.jsonl", self._docs)):
+                    with open(self._f(stem, new), "wb") as f:
+                        f.write(b"\n".join(x if isinstance(x, bytes) else
+                                           (b"null" if x is None else json.dumps(x, separators=(",", ":")).encode("utf-8"))
+                                           for x in items))
+                        f.write(b"\n")
+                if self._filters:
+                    if hasattr(ix, "get_filter_words_range"):
+                        words = ix.get_filter_words_range(0, n)
+                    else:
+                        from .index import bits_to_words
+                        words = bits_to_words([ix.get_filter_bits(r) for r in range(n)])
+                    if words.any():
+                        words.tofile(self._f("masks.u64", new))
+            if self._log is not None:
+                self._log.close()
+                self._vec.close()
+            self._write_manifest(**extra)               # the switch
+            self._gen = new
+            for stem in ("rows.bin", "ids.txt", "meta.jsonl", "docs.jsonl", "masks.u64", "oplog.jsonl", "oplog.vec"):
+                try:
+                    os.remove(self._f(stem, old))
+                except OSError:
+                    pass
+            self._log = open(self._f("oplog.jsonl"), "ab")
+            self._vec = open(self._f("oplog.vec"), "ab")
+            self._log_ops = self._log_rows = 0
+            self._snap_rows = n
 
     # ------------------------------------------------------------------ add
     def add(self, ids, embeddings, metadatas=None, documents=None):
@@ -236,32 +470,29 @@ class Collection:
                 return
             if len(keep) != n:
                 rows = rows[keep]
-            self._add_rows([ids[i] for i in keep], rows, [metadatas[i] for i in keep],
-                           [documents[i] for i in keep], log=True)
-
-    def _add_rows(self, ids, rows, metadatas, documents, log: bool):
-        ix = self._ensure_index(int(rows.shape[1]))
-        first = ix.add(rows)
-        assert first == len(self._ids), "host/device row bookkeeping diverged"
-        if log and self._log is not None and not isinstance(rows, np.ndarray):
-            rows = rows.cpu().numpy()                 # the persistence log stores the f32 rows
-        elif not isinstance(rows, np.ndarray):
-            rows = _NoRows(int(rows.shape[1]))
-        with_bits = False
-        for j, id_ in enumerate(ids):
-            self._row_of[id_] = first + j
-            self._ids.append(id_)
-            self._metas.append(dict(metadatas[j]) if metadatas[j] is not None else None)
-            self._docs.append(documents[j])
-            if metadatas[j] and FILTER_JSON_KEY in metadatas[j]:
-                with_bits = True
-            if log:
-                self._log_op({"op": "add", "id": id_, "dim": int(rows.shape[1]), "metadata": metadatas[j],
-                              "document": documents[j]}, rows[j])
-        if with_bits:      # one bulk copy (one collective on a ShardedIndex) instead of one call per row
-            self._index.set_filter_bits_range(first, [self._filter_bits_of(first + j) for j in range(len(ids))])
-        if log:
+                ids, metadatas, documents = [ids[i] for i in keep], [metadatas[i] for i in keep], [documents[i] for i in keep]
+            self._add_rows(ids, rows, metadatas, documents, log=True)
             self._log_flush()
+
+    def _add_rows(self, ids, rows, metadatas, documents, log: bool, raw: bool = False):
+        ix = self._ensure_index(int(rows.shape[1]))
+        first = ix.add_raw(rows) if raw else ix.add(rows)
+        assert first == len(self._ids), "host/device row bookkeeping diverged"
+        n = len(ids)
+        self._ids.extend(ids)
+        self._row_of.update(zip(ids, range(first, first + n)))
+        self._metas.extend(dict(m) if m is not None else None for m in metadatas)
+        self._docs.extend(documents)
+        if any(m and FILTER_JSON_KEY in m for m in metadatas):
+            # one bulk copy (one call per shard) instead of one call per row
+            self._index.set_filter_bits_range(first, [self._json_bits_of(m)[0] for m in metadatas])
+        if log and self._log is not None:
+            # the log keeps the rows exactly as stored (bf16 stays bf16): a replay re-creates the same bits
+            stored = ix.get_raw(first, n) if hasattr(ix, "get_raw") else \
+                (rows if isinstance(rows, np.ndarray) else rows.cpu().numpy())
+            self._log_op({"op": "add", "ids": list(ids),
+                          "metadatas": None if all(m is None for m in metadatas) else list(metadatas),
+                          "documents": None if all(d is None for d in documents) else list(documents)}, stored)
 
     # ------------------------------------------------------------------ query
     def query(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None,
@@ -323,53 +554,47 @@ class Collection:
                                                                                    require_bits=require, mode=mode))
 
     def _run_query(self, B, n_results, include, where_filters, filter_mode, run):
-        if True:
-            count = len(self._ids)
-            out: Dict[str, Any] = {"ids": [[] for _ in range(B)], "embeddings": None, "documents": None,
-                                   "metadatas": None, "distances": None, "uris": None, "data": None,
-                                   "included": include}
-            for key in ("metadatas", "documents", "distances", "embeddings"):
-                if key in include:
-                    out[key] = [[] for _ in range(B)]
-            if count == 0:
-                return out
-            k = min(int(n_results), count)
-            require = None
-            if where_filters and filter_mode == "pre":
-                require = []
-                for f in where_filters:
-                    b = self._filter_bit(f, create=False)
-                    if b is None:
-                        return out          # nobody answered this filter: nothing can match
-                    require.append(b)
-            scores, rows = run(k, require)
-            for b in range(B):
-                for s, r in zip(scores[b].tolist(), rows[b].tolist()):
-                    if r < 0:
-                        continue
-                    r -= self._row_base
-                    if where_filters and filter_mode == "post" and not self._passes(r, where_filters):
-                        continue
-                    out["ids"][b].append(self._ids[r])
-                    if out["distances"] is not None:
-                        out["distances"][b].append(1.0 - s)
-                    if out["metadatas"] is not None:
-                        m = self._metas[r]
-                        out["metadatas"][b].append(dict(m) if m is not None else None)
-                    if out["documents"] is not None:
-                        out["documents"][b].append(self._docs[r])
-                    if out["embeddings"] is not None:
-                        out["embeddings"][b].append(self._index.get_rows(r, 1)[0].tolist())
+        count = len(self._ids)
+        out: Dict[str, Any] = {"ids": [[] for _ in range(B)], "embeddings": None, "documents": None,
+                               "metadatas": None, "distances": None, "uris": None, "data": None,
+                               "included": include}
+        for key in ("metadatas", "documents", "distances", "embeddings"):
+            if key in include:
+                out[key] = [[] for _ in range(B)]
+        if count == 0:
             return out
+        k = min(int(n_results), count)
+        require = None
+        if where_filters and filter_mode == "pre":
+            require = []
+            for f in where_filters:
+                b = self._filter_bit(f, create=False)
+                if b is None:
+                    return out          # nobody answered this filter: nothing can match
+                require.append(b)
+        scores, rows = run(k, require)
+        for b in range(B):
+            for s, r in zip(scores[b].tolist(), rows[b].tolist()):
+                if r < 0:
+                    continue
+                r -= self._row_base
+                if where_filters and filter_mode == "post" and not self._passes(r, where_filters):
+                    continue
+                out["ids"][b].append(self._ids[r])
+                if out["distances"] is not None:
+                    out["distances"][b].append(1.0 - s)
+                if out["metadatas"] is not None:
+                    out["metadatas"][b].append(self._meta_out(r))
+                if out["documents"] is not None:
+                    out["documents"][b].append(self._doc(r))
+                if out["embeddings"] is not None:
+                    out["embeddings"][b].append(self._index.get_rows(r, 1)[0].tolist())
+        return out
 
     def _passes(self, row: int, filters: Iterable[str]) -> bool:
-        meta = self._metas[row] or {}
-        try:
-            answers = json.loads(meta[FILTER_JSON_KEY]) if FILTER_JSON_KEY in meta else {}
-        except (json.JSONDecodeError, TypeError):
-            answers = {}
-        if not isinstance(answers, dict):
-            answers = {}
+        answers = _answers_of(self._meta(row))
+        if self._swept:
+            answers.update(self._swept_answers(row))
         return all(_yes(answers.get(f, "")) for f in filters)
 
     # ------------------------------------------------------------------ get / count
@@ -384,7 +609,7 @@ class Collection:
         include = list(include)
         with self._lock:
             if ids is None:
-                rows = list(range(len(self._ids)))
+                rows = range(len(self._ids))
             else:
                 if isinstance(ids, str):
                     ids = [ids]
@@ -396,9 +621,9 @@ class Collection:
             out: Dict[str, Any] = {"ids": [self._ids[r] for r in rows], "embeddings": None, "documents": None,
                                    "metadatas": None, "uris": None, "data": None, "included": include}
             if "metadatas" in include:
-                out["metadatas"] = [dict(self._metas[r]) if self._metas[r] is not None else None for r in rows]
+                out["metadatas"] = [self._meta_out(r) for r in rows]
             if "documents" in include:
-                out["documents"] = [self._docs[r] for r in rows]
+                out["documents"] = [self._doc(r) for r in rows]
             if "embeddings" in include:
                 out["embeddings"] = [self._index.get_rows(r, 1)[0] for r in rows]
             return out
@@ -435,7 +660,7 @@ class Collection:
                 if rows is not None:
                     # re-embed: delete + add keeps the slab dense (row number changes, id does not)
                     r = self._row_of[id_]
-                    meta, doc = self._metas[r], self._docs[r]
+                    meta, doc = self._meta(r), self._doc(r)
                     self._delete_ids([id_], log=True)
                     self._add_rows([id_], rows[j:j + 1], [meta], [doc], log=True)
                 self._update_one(id_, metadatas[j], documents[j], log=True)
@@ -446,7 +671,7 @@ class Collection:
         if r is None:
             return
         if metadata is not None:
-            merged = dict(self._metas[r] or {})
+            merged = dict(self._meta(r) or {})
             merged.update(metadata)
             self._metas[r] = merged
             if FILTER_JSON_KEY in metadata:
@@ -457,7 +682,8 @@ class Collection:
             self._log_op({"op": "update", "id": id_, "metadata": metadata, "document": document})
 
     def delete(self, ids=None, where=None, where_document=None):
-        """``collection.delete(ids=all_ids)`` (backend/app/main.py:1069)."""
+        """``collection.delete(ids=all_ids)`` (backend/app/main.py:1069): any number of ids costs ONE
+        compaction kernel and one synchronise per shard; deleting everything just drops the row count."""
         if where is not None or where_document is not None:
             raise NotImplementedError("where / where_document are not used by the reference and not implemented")
         with self._lock:
@@ -469,19 +695,35 @@ class Collection:
             self._log_flush()
 
     def _delete_ids(self, ids: List[str], log: bool):
-        for id_ in ids:
-            r = self._row_of.pop(id_, None)
-            if r is None:
-                continue
-            moved = self._index.remove(r)
-            last = len(self._ids) - 1
-            assert moved in (-1, last)
-            if r != last:
-                self._ids[r], self._metas[r], self._docs[r] = self._ids[last], self._metas[last], self._docs[last]
-                self._row_of[self._ids[r]] = r
-            self._ids.pop(); self._metas.pop(); self._docs.pop()
-            if log:
-                self._log_op({"op": "delete", "id": id_})
+        rows = sorted({self._row_of[i] for i in ids if i in self._row_of})
+        if not rows:
+            return
+        n = len(self._ids)
+        gone = [self._ids[r] for r in rows]
+        if len(rows) == n:                               # reset_system (main.py:1065-1069)
+            self._index.clear()
+            self._ids, self._metas, self._docs, self._row_of = [], [], [], {}
+        elif len(rows) == 1 or not hasattr(self._index, "remove_rows"):
+            for r in reversed(rows):                     # descending: earlier moves never touch later holes
+                moved = self._index.remove(r)
+                last = len(self._ids) - 1
+                assert moved in (-1, last)
+                del self._row_of[self._ids[r]]
+                if r != last:
+                    self._ids[r], self._metas[r], self._docs[r] = self._ids[last], self._metas[last], self._docs[last]
+                    self._row_of[self._ids[r]] = r
+                self._ids.pop(); self._metas.pop(); self._docs.pop()
+        else:
+            src, dst = self._index.remove_rows(np.asarray(rows, dtype=np.int64))
+            for i in gone:
+                del self._row_of[i]
+            for s, d in zip(src.tolist(), dst.tolist()):
+                self._ids[d], self._metas[d], self._docs[d] = self._ids[s], self._metas[s], self._docs[s]
+                self._row_of[self._ids[d]] = d
+            new_n = n - len(rows)
+            del self._ids[new_n:], self._metas[new_n:], self._docs[new_n:]
+        if log:
+            self._log_op({"op": "delete", "ids": gone})
 
     # ------------------------------------------------------------------ north_star extensions
     def filter_names(self) -> List[str]:
@@ -500,21 +742,70 @@ class Collection:
             return np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
 
     def apply_filter_sweep(self, filter_name: str, prompt_embedding, tau: float) -> int:
-        """Run the sweep for one prompt and store the outcome the way the reference stores
-        Moondream's answers (main.py:1010-1033): ``filter_results_json[filter_name] = "yes"|"no"``
-        for every row, plus the device filter bit.  Returns the number of "yes" rows."""
+        """The CLIP-side counterpart of ``process_filter_on_all_images`` (backend/app/main.py:939-1056):
+        one prompt embedding is swept over ALL rows on tensor cores and the outcome becomes the rows'
+        answers for ``filter_name``.  The answers are written where the query kernels test them -- filter
+        bit of every row, set by one kernel per GPU, nothing per row on the host -- and are materialised
+        as ``filter_results_json[filter_name] = "yes" | "no"`` whenever metadata is read (get / query /
+        the post-filter), so the reference's filter pass and UI see what the Moondream loop would have
+        stored.  ``filter_progress[filter_name]`` follows the reference's progress contract
+        (main.py:964-986, 1040-1056).  Returns the number of "yes" rows."""
         with self._lock:
-            mask = self.filter_sweep(prompt_embedding, tau)[0]
-            for r, hit in enumerate(mask.tolist()):
-                meta = dict(self._metas[r] or {})
-                try:
-                    answers = json.loads(meta.get(FILTER_JSON_KEY, "{}"))
-                except (json.JSONDecodeError, TypeError):
-                    answers = {}
-                answers[filter_name] = "yes" if hit else "no"
-                self._update_one(self._ids[r], {FILTER_JSON_KEY: json.dumps(answers)}, None, log=True)
-            self._log_flush()
-            return int(mask.sum())
+            total = len(self._ids)
+            self.filter_progress[filter_name] = {"status": "processing", "progress": 0, "current_image": "",
+                                                 "processed": 0, "total": total}
+            try:
+                bit = self._filter_bit(filter_name, create=True)
+                n_yes = 0
+                if total:
+                    p = _as_rows(prompt_embedding, self.dim)[0]
+                    if hasattr(self._index, "apply_filter_sweep"):
+                        n_yes = int(self._index.apply_filter_sweep(p, float(tau), bit))
+                    else:                                 # an index without the device-side write: bits via the host
+                        mask = self.filter_sweep(p[None], tau)[0]
+                        from .index import bits_to_words
+                        cur = [set(self._index.get_filter_bits(r)) for r in range(total)]
+                        self._index.set_filter_bits_range(0, [sorted((c - {bit}) | ({bit} if h else set()))
+                                                              for c, h in zip(cur, mask.tolist())])
+                        n_yes = int(mask.sum())
+                self._swept.add(filter_name)
+                if self._log is not None:
+                    words = self._column_bits(bit, total)
+                    self._log_op({"op": "sweep", "name": filter_name, "bit": bit, "n": total,
+                                  "bits": base64.b64encode(words.tobytes()).decode("ascii")})
+                    self._log_flush()
+                self.filter_progress[filter_name] = {"status": "completed", "progress": 100, "processed": total,
+                                                     "total": total, "matched": n_yes}
+                return n_yes
+            except Exception as e:
+                self.filter_progress[filter_name] = {"status": "error", "message": str(e), "progress": 0}
+                raise
+
+    def _column_bits(self, bit: int, n: int) -> np.ndarray:
+        """Packed (uint8, little bit order) column ``bit`` of the rows' filter words."""
+        ix = self._index
+        if hasattr(ix, "get_filter_words_range"):
+            col = (ix.get_filter_words_range(0, n)[:, bit // 64] >> np.uint64(bit % 64)) & np.uint64(1)
+            return np.packbits(col.astype(np.uint8), bitorder="little")
+        return np.packbits(np.array([bit in ix.get_filter_bits(r) for r in range(n)], dtype=np.uint8), bitorder="little")
+
+    def _replay_sweep(self, op: Dict[str, Any]):
+        n, bit = int(op["n"]), int(op["bit"])
+        while len(self._filters) <= bit:
+            self._filters.append(op["name"] if len(self._filters) == bit else f"__unused_{len(self._filters)}")
+        self._swept.add(op["name"])
+        if n == 0 or n != len(self._ids):
+            return
+        yes = np.unpackbits(np.frombuffer(base64.b64decode(op["bits"]), dtype=np.uint8), bitorder="little")[:n].astype(bool)
+        ix = self._index
+        if hasattr(ix, "get_filter_words_range"):
+            words = ix.get_filter_words_range(0, n)
+            m = np.uint64(1 << (bit % 64))
+            words[:, bit // 64] = np.where(yes, words[:, bit // 64] | m, words[:, bit // 64] & ~m)
+            ix.set_filter_words_range(0, words)
+        else:
+            ix.set_filter_bits_range(0, [sorted((set(ix.get_filter_bits(r)) - {bit}) | ({bit} if y else set()))
+                                         for r, y in enumerate(yes.tolist())])
 
     def find_duplicates(self, threshold: float = 0.95):
         """All pairs of stored embeddings with cosine >= threshold (BASELINE config 5):
@@ -528,7 +819,8 @@ class Collection:
     def close(self):
         with self._lock:
             if self._log is not None:
-                self._log_flush()
+                if self._log_ops > 0:
+                    self.persist()                      # fold the log: the next open is one slab upload
                 self._log.close(); self._vec.close()
                 self._log = None
             if self._index is not None:
@@ -538,17 +830,29 @@ class Collection:
 
 class PersistentClient:
     """``chromadb.PersistentClient(path=...)`` as used at backend/app/utils.py:113 and
-    init_db.py:36: collections persist under ``path/<name>/`` as an append-only operation log +
-    raw float32 vectors and are re-ingested onto the GPU when reopened."""
+    init_db.py:36: collections persist under ``path/<name>/`` (snapshot + operation log, see the module
+    docstring) and are uploaded to the GPU(s) when reopened.  ``devices=[...]`` makes every collection a
+    single-process multi-GPU one (``GroupIndex``)."""
 
-    def __init__(self, path: str = "./chroma", *, device: int = 0, dtype: str = "f32"):
+    def __init__(self, path: str = "./chroma", *, device: int = 0, dtype: str = "f32",
+                 devices: Optional[Sequence[int]] = None, durable: bool = False):
         self.path = path
-        self._device, self._dtype = device, dtype
+        self._device, self._dtype, self._devices, self._durable = device, dtype, devices, durable
         os.makedirs(path, exist_ok=True)
         self._open: Dict[str, Collection] = {}
 
     def _dir(self, name: str) -> str:
         return os.path.join(self.path, name)
+
+    def _factory(self, dtype: str):
+        if self._devices is None:
+            return None
+        devices = list(self._devices)
+
+        def make(dim: int):
+            from .group_index import GroupIndex
+            return GroupIndex(dim, dtype, devices=devices)
+        return make
 
     def list_collections(self) -> List[str]:
         """Names only -- the reference does ``COLLECTION_NAME in client.list_collections()``
@@ -562,11 +866,16 @@ class PersistentClient:
             if get_or_create:
                 return self.get_collection(name)
             raise ValueError(f"Collection {name} already exists")
+        space = (metadata or {}).get("hnsw:space", "cosine")
+        if space != "cosine":
+            raise ValueError(f"only the cosine space is implemented (got hnsw:space={space!r})")
         d = self._dir(name)
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "collection.json"), "w", encoding="utf-8") as f:
-            json.dump({"name": name, "metadata": metadata or {}, "dtype": self._dtype}, f)
-        c = Collection(name, metadata, device=self._device, dtype=self._dtype, path=d)
+            json.dump({"name": name, "metadata": metadata or {}, "dtype": self._dtype, "format": FORMAT_VERSION,
+                       "gen": 0, "count": 0}, f)
+        c = Collection(name, metadata, device=self._device, dtype=self._dtype, path=d,
+                       index_factory=self._factory(self._dtype), durable=self._durable)
         self._open[name] = c
         return c
 
@@ -579,7 +888,9 @@ class PersistentClient:
             raise ValueError(f"Collection {name} does not exist.")
         with open(cfg, "r", encoding="utf-8") as f:
             info = json.load(f)
-        c = Collection(name, info.get("metadata"), device=self._device, dtype=info.get("dtype", self._dtype), path=d)
+        dtype = info.get("dtype", self._dtype)
+        c = Collection(name, info.get("metadata"), device=self._device, dtype=dtype, path=d,
+                       index_factory=self._factory(dtype), durable=self._durable)
         self._open[name] = c
         return c
 

@@ -7,8 +7,12 @@
 //               EVERY rank's buffer (plain st.global on peer-mapped addresses -> NVLink writes),
 //   2. signal : __threadfence_system, then st.release.sys of `epoch` into flag [slot][rank] of
 //               every rank,
-//   3. wait   : ld.acquire.sys spin on the G LOCAL flags of the slot (bounded, sets *err),
+//   3. wait   : ld.acquire.sys spin on the G LOCAL flags of the slot (bounded),
 //   4. merge  : merges the G lists that now sit in LOCAL memory into its register top-k list.
+// A wait that times out (a peer never arrived within ~3 s) NEVER merges: the half-buffer may still
+// hold lists of exchange e-2, so the slot's result is written as empty (-inf, -1) and the sticky
+// error word -- host-mapped pinned memory, so every host entry point can test it without a CUDA
+// call -- is raised; the host APIs turn it into VS_ERR_EXCHANGE.
 // Steps 3+4 may be deferred: a batch of independent queries pushes into distinct slots of ONE epoch
 // (push_only) and a single collect kernel waits for + merges all of them, so the ranks meet once
 // per batch instead of once per query (per-query rendezvous makes every query as slow as the
@@ -27,7 +31,7 @@ constexpr int kMaxPeers = 8;
 
 struct XchgParams {
   unsigned char* peers[kMaxPeers];   // peer-mapped base pointers; peers[rank] is the local buffer
-  unsigned int* err;                 // device flag: set to 1 when a wait timed out
+  unsigned int* err;                 // sticky error word in host-mapped pinned memory: 1 = a wait timed out
   int G;                             // 0 = no exchange
   int rank;
   int Bmax, kmax;
@@ -71,12 +75,14 @@ __device__ __forceinline__ void xchg_push(const XchgParams& x, const WarpTopK<M>
   }
 }
 
-// steps 3 + 4 (warp-collective): `top` is re-initialised and receives the global top-k.
+// steps 3 + 4 (warp-collective): `top` is re-initialised and receives the global top-k, or stays
+// empty when a peer never arrived (see the header comment).
 template <int M>
 __device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>& top, int slot, int k, int lane) {
   const XchgLayout L = xchg_layout(x.Bmax, x.kmax, x.G);
   const size_t half = (size_t)(x.epoch & 1u) * L.half_bytes;
   const unsigned char* mine = x.peers[x.rank] + half;
+  bool timed_out = false;
   if (lane < x.G) {
     const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine) + (size_t)slot * kMaxPeers + lane;
     const long long t0 = clock64();
@@ -85,14 +91,20 @@ __device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
       if (v == x.epoch) break;
       if (clock64() - t0 > 6000000000LL) {   // ~3 s: a peer never arrived
-        atomicExch(x.err, 1u);
+        timed_out = true;
         break;
       }
       __nanosleep(64);
     }
   }
-  __syncwarp();
   top.init();
+  if (__any_sync(0xffffffffu, timed_out)) {
+    if (lane == 0) {
+      *reinterpret_cast<volatile unsigned int*>(x.err) = 1u;
+      __threadfence_system();
+    }
+    return;
+  }
   const volatile float* ls = reinterpret_cast<const volatile float*>(mine + L.scores_off) + (size_t)slot * x.kmax;
   const volatile uint32_t* lr = reinterpret_cast<const volatile uint32_t*>(mine + L.rows_off) + (size_t)slot * x.kmax;
   top.merge_from(ls, lr, x.G, x.Bmax * x.kmax, k, lane);

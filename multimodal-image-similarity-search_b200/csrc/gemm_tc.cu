@@ -755,20 +755,6 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   for (int e = lane; e < Dp; e += 32) o[e] = __float2bfloat16_rn(e < dim ? s[e] * inv : 0.f);
 }
 
-// gmin[g] = (1 - 2^-20) * min over the valid rows of 32-row group g of the row norm 1/inv_norm
-// (+inf for a group with no valid row); see the fast-reject test in the epilogue.
-__global__ void __launch_bounds__(256) group_min_norm_kernel(const float* __restrict__ inv, uint32_t n_rows,
-                                                             uint32_t n_groups, float* __restrict__ gmin) {
-  const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (g >= n_groups) return;
-  const uint32_t row = g * 32 + (threadIdx.x & 31);
-  float nrm = __int_as_float(0x7f800000);
-  if (row < n_rows) nrm = 1.0f / __ldg(inv + row);
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) nrm = fminf(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
-  if ((threadIdx.x & 31) == 0) gmin[g] = nrm * (1.0f - 9.5367431640625e-07f);
-}
-
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -787,8 +773,6 @@ static EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
-
-bool tensor_path_available() { return true; }
 
 // bf16 [rows][ld] row-major, box = 64 k-elements x box_rows, 128B swizzle, zero fill out of bounds
 static cudaError_t make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, uint64_t ld_elems,
@@ -895,26 +879,21 @@ static int cluster_for(int chunks) {
   return c;
 }
 
-// workspace layout: [gmin f32 x groups][gbound u32 x Bp][queries bf16 Bp x Dp][partial lists]
+// workspace layout: [gbound u32 x Bp][queries bf16 Bp x Dp][partial lists]
 struct TcWorkspace {
-  float* gmin;
   uint32_t* gbound;
   __nv_bfloat16* q;
   float* parts;
-  uint32_t n_groups;
   size_t total;
 };
-static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_count, int64_t n_rows) {
+static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_count) {
   const TcPlan pl = plan_for(dim);
   const int Bp = (B + kTcM - 1) / kTcM * kTcM;
   const int KL = kl_for(k);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   TcWorkspace w;
-  w.n_groups = (uint32_t)((n_rows + 255) / 256 * 8);   // whole 256-row tiles
   char* p = static_cast<char*>(base);
   size_t off = 0;
-  w.gmin = reinterpret_cast<float*>(p + off);
-  off += up((size_t)w.n_groups * 4);
   w.gbound = reinterpret_cast<uint32_t*>(p + off);
   off += up((size_t)Bp * 32 * 4);   // union pool: up to 32 keys per query
   w.q = reinterpret_cast<__nv_bfloat16*>(p + off);
@@ -924,12 +903,8 @@ static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_cou
   w.total = off;
   return w;
 }
-size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count, int64_t n_rows) {
-  return carve_workspace(nullptr, B, dim, k, sm_count, n_rows).total;
-}
-static void launch_gmin(const TensorArgs& a, const TcWorkspace& w, cudaStream_t st) {
-  group_min_norm_kernel<<<(w.n_groups + 7) / 8, 256, 0, st>>>(a.inv_norm, (uint32_t)a.n_rows, w.n_groups, w.gmin);
-  count_launch();
+size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count) {
+  return carve_workspace(nullptr, B, dim, k, sm_count).total;
 }
 static int tc_prefetch() {
   static int v = env_int("VS_TC_PREFETCH", 0);   // measured on B200: no gain for top-k, a loss for the sweep
@@ -1046,14 +1021,14 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
   if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || B <= 0) return cudaErrorNotSupported;
   const int Bp = (B + kTcM - 1) / kTcM * kTcM;
   const int KL = kl_for(k);
-  const TcWorkspace ws = carve_workspace(workspace, B, a.dim, k, sm_count, a.n_rows);
+  const TcWorkspace ws = carve_workspace(workspace, B, a.dim, k, sm_count);
   __nv_bfloat16* qb = ws.q;
   float* part_s = ws.parts;
 
   const int KLP = pool_stride(KL);
   prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb, ws.gbound, KLP);
   count_launch();
-  launch_gmin(a, ws, st);
+  if (!a.gmin) return cudaErrorInvalidValue;
 
   const int chunks_total = Bp / kTcM;
   for (int c0 = 0; c0 < chunks_total;) {
@@ -1062,7 +1037,7 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
     const TcPlan plc = plan_for_cg(a.dim, cg);
     TcParams p;
     fill_common(p, a, plc);
-    p.gmin = ws.gmin;
+    p.gmin = a.gmin;
     p.gbound = ws.gbound + (size_t)c0 * kTcM * KLP;
     p.k_real = k;
     static const int pool_mode = env_int("VS_TC_POOL", 1);
@@ -1108,7 +1083,7 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a) || F <= 0) return cudaErrorNotSupported;
   const int Bp = (F + kTcM - 1) / kTcM * kTcM;
-  const TcWorkspace ws = carve_workspace(workspace, F, a.dim, 1, sm_count, a.n_rows);
+  const TcWorkspace ws = carve_workspace(workspace, F, a.dim, 1, sm_count);
   __nv_bfloat16* qb = ws.q;
   prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb, nullptr, 0);
   count_launch();
@@ -1142,8 +1117,8 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
                                 void* workspace, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a)) return cudaErrorNotSupported;
-  const TcWorkspace ws = carve_workspace(workspace, kTcM, a.dim, 1, sm_count, a.n_rows);
-  launch_gmin(a, ws, st);
+  (void)workspace;
+  if (!a.gmin) return cudaErrorInvalidValue;
   const int64_t a_row_min = row_lo;
   row_lo = row_lo / kTcM * kTcM;   // A blocks are 128-row aligned; rows below the caller's row_lo are filtered out
   const int n_blocks = (int)((row_hi - row_lo + kTcM - 1) / kTcM);
@@ -1152,7 +1127,7 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
   const TcPlan plc = plan_for_cg(a.dim, cg);
   TcParams p;
   fill_common(p, a, plc);
-  p.gmin = ws.gmin;
+  p.gmin = a.gmin;
   p.a_row_min = a_row_min;
   p.a_row_lo = row_lo;
   p.a_row_hi = row_hi;

@@ -59,6 +59,39 @@ cudaError_t launch_ingest(const float* src, int64_t n, int dim, int dtype, void*
   return cudaGetLastError();
 }
 
+// inverse norms of rows that are ALREADY in the storage dtype (persistence slab reload, vs_add_raw_host):
+// the same arithmetic as ingest_kernel applied to the stored values, so a reloaded collection scores
+// bit-identically to the one that was saved.
+template <typename T>
+__global__ void __launch_bounds__(256) renorm_kernel(const T* __restrict__ rows, int64_t first, int64_t n, int dim, int64_t ld,
+                                                     float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const T* r = rows + (first + i) * ld;
+    float ss = 0.f;
+    for (int e = lane; e < (int)ld; e += 32) {
+      const float v = e < dim ? (float)r[e] : 0.f;
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if (lane == 0) inv[first + i] = 1.0f / (sqrtf(ss) + 1e-30f);
+  }
+}
+cudaError_t launch_renorm(const void* rows, int64_t first, int64_t n, int dim, int dtype, int64_t ld_elems, float* inv,
+                          cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t blocks = min((int64_t)148 * 8, (n + 7) / 8);
+  if (dtype == 0)
+    renorm_kernel<float><<<(int)blocks, 256, 0, st>>>(static_cast<const float*>(rows), first, n, dim, ld_elems, inv);
+  else
+    renorm_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(rows), first, n, dim, ld_elems, inv);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) export_kernel(const T* __restrict__ rows, int64_t n, int dim, int64_t ld,
                                                      float* __restrict__ dst) {
@@ -124,6 +157,103 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ im
     const float c = out[(size_t)b * dim + e];
     out[(size_t)b * dim + e] = nc > 0.f ? c / nc : 0.f;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Store maintenance (Collection.delete, backend/app/main.py:1069; reset :1058-1098).
+// move_rows: for every (src, dst) pair copy the stored row, its inverse norm and its filter bits
+// src -> dst.  The host guarantees {src} and {dst} are disjoint (sources are surviving tail rows,
+// destinations are holes below the new count), so ONE launch compacts any number of deletions.
+// One warp per pair, 16-byte chunks.  `src_*` may be peer-mapped memory of another GPU (vs_copy_row).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) move_rows_kernel(const uint4* src_rows, const float* src_inv, const uint64_t* src_mask,
+                                                        uint4* dst_rows, float* dst_inv, uint64_t* dst_mask,
+                                                        const int64_t* __restrict__ pairs, int64_t n_pairs, int chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w0; i < n_pairs; i += nw) {
+    const int64_t s = pairs[2 * i], d = pairs[2 * i + 1];
+    for (int c = lane; c < chunks; c += 32) dst_rows[d * chunks + c] = src_rows[s * chunks + c];
+    if (lane == 0) dst_inv[d] = src_inv[s];
+    if (dst_mask && lane < kMaskWords) dst_mask[d * kMaskWords + lane] = src_mask ? src_mask[s * kMaskWords + lane] : 0ull;
+  }
+}
+cudaError_t launch_move_rows(const void* src_rows, const float* src_inv, const uint64_t* src_mask, void* dst_rows,
+                             float* dst_inv, uint64_t* dst_mask, const int64_t* pairs_dev, int64_t n_pairs, int64_t ld_bytes,
+                             cudaStream_t st) {
+  if (n_pairs <= 0) return cudaSuccess;
+  const int64_t blocks = min((int64_t)148 * 8, (n_pairs + 7) / 8);
+  move_rows_kernel<<<(int)blocks, 256, 0, st>>>(static_cast<const uint4*>(src_rows), src_inv, src_mask,
+                                                 static_cast<uint4*>(dst_rows), dst_inv, dst_mask, pairs_dev, n_pairs,
+                                                 (int)(ld_bytes / 16));
+  count_launch();
+  return cudaGetLastError();
+}
+
+// dst row (dst_first + l * dst_stride) <- src row l for l in [0, n): raw storage (rows, inverse norms).
+// Runs on the DESTINATION device and reads the source shard through NVLink peer memory: this is how the
+// row-striped shards of a vs_group are replicated into one full index per GPU for the all-pairs pass.
+__global__ void __launch_bounds__(256) strided_copy_kernel(const uint4* __restrict__ src_rows, const float* __restrict__ src_inv,
+                                                           uint4* __restrict__ dst_rows, float* __restrict__ dst_inv, int64_t n,
+                                                           int64_t dst_first, int64_t dst_stride, int chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t l = w0; l < n; l += nw) {
+    const int64_t d = dst_first + l * dst_stride;
+    for (int c = lane; c < chunks; c += 32) dst_rows[d * chunks + c] = src_rows[l * chunks + c];
+    if (lane == 0) dst_inv[d] = src_inv[l];
+  }
+}
+cudaError_t launch_strided_copy(const void* src_rows, const float* src_inv, void* dst_rows, float* dst_inv, int64_t n,
+                                int64_t dst_first, int64_t dst_stride, int64_t ld_bytes, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t blocks = min((int64_t)148 * 16, (n + 7) / 8);
+  strided_copy_kernel<<<(int)blocks, 256, 0, st>>>(static_cast<const uint4*>(src_rows), src_inv, static_cast<uint4*>(dst_rows),
+                                                    dst_inv, n, dst_first, dst_stride, (int)(ld_bytes / 16));
+  count_launch();
+  return cudaGetLastError();
+}
+
+// Filter sweep -> stored filter bits without leaving the device (the CLIP-side analogue of the answers
+// written at backend/app/main.py:1010-1033): bit `bit` of row r := bit r of the sweep's word array.
+__global__ void __launch_bounds__(256) apply_sweep_bits_kernel(const uint32_t* __restrict__ words, int64_t n, int bit,
+                                                               uint64_t* __restrict__ mask) {
+  const uint64_t m = 1ull << (bit & 63);
+  const int w = bit >> 6;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const bool yes = (words[r >> 5] >> (r & 31)) & 1u;
+    uint64_t* p = mask + r * kMaskWords + w;
+    *p = yes ? (*p | m) : (*p & ~m);
+  }
+}
+cudaError_t launch_apply_sweep_bits(const uint32_t* words, int64_t n, int bit, uint64_t* mask, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  apply_sweep_bits_kernel<<<(int)min((int64_t)148 * 8, (n + 255) / 256), 256, 0, st>>>(words, n, bit, mask);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// gmin[g] = (1 - 2^-20) * min over the valid rows of 32-row group g of the row norm 1/inv_norm
+// (+inf for a group with no valid row); the tcgen05 epilogues' fast-reject bound (gemm_tc.cu).
+// Kept current by every mutation of the index (api.cu: refresh_gmin), so no query pays for it.
+__global__ void __launch_bounds__(256) group_min_norm_kernel(const float* __restrict__ inv, uint32_t n_rows, uint32_t g_lo,
+                                                             uint32_t g_hi, float* __restrict__ gmin) {
+  const uint32_t g = g_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= g_hi) return;
+  const uint32_t row = g * 32 + (threadIdx.x & 31);
+  float nrm = __int_as_float(0x7f800000);
+  if (row < n_rows) nrm = 1.0f / __ldg(inv + row);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) nrm = fminf(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+  if ((threadIdx.x & 31) == 0) gmin[g] = nrm * (1.0f - 9.5367431640625e-07f);
+}
+cudaError_t launch_group_min(const float* inv, int64_t n_rows, int64_t g_lo, int64_t g_hi, float* gmin, cudaStream_t st) {
+  if (g_hi <= g_lo) return cudaSuccess;
+  group_min_norm_kernel<<<(unsigned)((g_hi - g_lo + 7) / 8), 256, 0, st>>>(inv, (uint32_t)n_rows, (uint32_t)g_lo, (uint32_t)g_hi, gmin);
+  count_launch();
+  return cudaGetLastError();
 }
 
 __global__ void fill_empty_kernel(float* s, int64_t* r, int64_t n) {

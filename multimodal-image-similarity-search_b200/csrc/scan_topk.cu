@@ -68,6 +68,9 @@ struct ScanKernelParams {
   int stages;
   int stage_stride;   // bytes between row stages
   int use_mask;
+  int early_wait;     // 1: griddepcontrol.wait before the first read of q / the corpus (see launch_one)
+  unsigned int* done_flag;   // host-mapped [B] or nullptr: done_flag[qi] = done_seq once query qi's result is written
+  unsigned int done_seq;
   XchgParams xg;      // xg.G > 0: exchange the shard's result with the peers before writing it
 };
 
@@ -94,6 +97,13 @@ __device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<
         p.out_s[(size_t)qi * k + e] = top.s[m];
         p.out_r[(size_t)qi * k + e] = top.r[m] == kEmptyRow ? -1 : (int64_t)top.r[m] * mul + add;
       }
+  }
+  if (p.done_flag) {
+    // request/response without a stream synchronise: out_s/out_r (and the flag) live in host-mapped
+    // pinned memory; the host thread polls the flag (vs_group_query_host)
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.done_flag + qi), "r"(p.done_seq) : "memory");
   }
 }
 
@@ -166,10 +176,14 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   }
   __syncthreads();
   // PDL: the next query's kernel may start filling SMs as this grid's CTAs retire.  This kernel
-  // only READS the corpus/query until the partial lists are written, so the wait on the previous
-  // grid (which may still be merging into the same workspace) is deferred to that point.
+  // only READS the corpus/query until the partial lists are written, so -- when the host knows that
+  // nothing this kernel reads was produced by the grid right before it in the stream (early_wait = 0:
+  // the previous launch was a scan of this library and the caller vouches for q, VS_Q_PIPELINED) --
+  // the wait on the previous grid (which may still be merging into the same workspace) is deferred
+  // to that point.  Otherwise the wait comes first: the PDL contract makes the primary's writes
+  // visible only after griddepcontrol.wait.
   pdl_launch_dependents();
-  if constexpr (M == 0) pdl_wait();   // the materialising variant writes shared scratch while scanning
+  if (M == 0 || p.early_wait) pdl_wait();   // (the materialising variant writes shared scratch while scanning)
 
   WarpTopK<ML> top;
   top.init();
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   }
 
   if constexpr (M == 0) return;
-  pdl_wait();   // previous grid fully done: its partial lists / tickets / result rows are no longer in use
+  if (!p.early_wait) pdl_wait();   // previous grid fully done: its partial lists / tickets / result rows are no longer in use
 
   // ---- per-CTA merge of the 8 warp lists ---------------------------------------------------
   if (warp < kConsumerWarps) top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
@@ -381,6 +395,9 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.dim = a.dim;
   p.ld_bytes = (int)a.ld_bytes;
   p.k = a.k;
+  p.early_wait = a.early_wait;
+  p.done_flag = a.done_flag;
+  p.done_seq = a.done_seq;
   p.xg = a.xg;
   p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
   const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;

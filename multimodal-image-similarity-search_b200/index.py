@@ -18,6 +18,23 @@ _DTYPES = {"f32": N.VS_F32, "fp32": N.VS_F32, "float32": N.VS_F32,
 _MODES = {"auto": N.VS_Q_AUTO, "scan": N.VS_Q_SCAN, "tensor": N.VS_Q_TENSOR}
 
 
+def _mode(mode: str, pipelined: bool = False) -> int:
+    """``pipelined``: the caller vouches that the query buffer was complete before the previous launch
+    on the stream (VS_Q_PIPELINED, see include/vecsearch_b200.h)."""
+    return _MODES[mode] | (N.VS_Q_PIPELINED if pipelined else 0)
+
+
+def bits_to_words(bits_lists: Sequence[Sequence[int]]) -> np.ndarray:
+    """Per-row filter-bit index lists -> uint64 [n, MASK_WORDS]."""
+    words = np.zeros((len(bits_lists), N.MASK_WORDS), dtype=np.uint64)
+    for j, bits in enumerate(bits_lists):
+        for b in bits:
+            if not 0 <= b < 64 * N.MASK_WORDS:
+                raise ValueError(f"filter bit {b} out of range [0,{64 * N.MASK_WORDS})")
+            words[j, b // 64] |= np.uint64(1 << (b % 64))
+    return words
+
+
 def _bits_array(bits: Optional[Sequence[int]]):
     """iterable of filter-bit indices -> (uint64 * 4) or None."""
     if bits is None:
@@ -49,11 +66,16 @@ def _stream_ptr(stream) -> int:
 
 class DeviceIndex:
     def __init__(self, dim: int, dtype: str = "f32", device: int = 0, capacity: int = 0, row_base: int = 0,
-                 row_stride: int = 1):
+                 row_stride: int = 1, _handle=None):
         self._lib = N.load()
         if dtype not in _DTYPES:
             raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
         self.dim, self.dtype, self.device = int(dim), "bf16" if _DTYPES[dtype] else "f32", int(device)
+        self._owned = _handle is None
+        if _handle is not None:                       # a shard of a vs_group_t: the group owns it
+            self._h = C.c_void_p(_handle)
+            self.device = int(self._lib.vs_device(self._h))
+            return
         h = C.c_void_p()
         N.check(self._lib.vs_create(self.device, self.dim, _DTYPES[dtype], int(capacity), C.byref(h)))
         self._h = h
@@ -63,7 +85,8 @@ class DeviceIndex:
     # -- lifecycle ---------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.vs_destroy(self._h)
+            if self._owned:
+                self._lib.vs_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -120,6 +143,59 @@ class DeviceIndex:
         N.check(self._lib.vs_remove(self._h, int(row), C.byref(moved)))
         return int(moved.value)
 
+    def remove_rows(self, rows) -> Tuple[np.ndarray, np.ndarray]:
+        """Remove many rows with ONE compaction kernel (vs_remove_rows).  Returns (moved_src, moved_dst):
+        surviving row ``moved_src[i]`` now lives at ``moved_dst[i]``; the new count is ``count - len(rows)``."""
+        r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+        m = int(r.shape[0])
+        src = np.empty(max(m, 1), dtype=np.int64)
+        dst = np.empty(max(m, 1), dtype=np.int64)
+        nm = C.c_int64(0)
+        N.check(self._lib.vs_remove_rows(self._h, r.ctypes.data, m, src.ctypes.data, dst.ctypes.data, C.byref(nm)))
+        return src[:nm.value].copy(), dst[:nm.value].copy()
+
+    def truncate(self, new_count: int):
+        N.check(self._lib.vs_truncate(self._h, int(new_count)))
+
+    def reserve(self, capacity: int):
+        N.check(self._lib.vs_reserve(self._h, int(capacity)))
+
+    def copy_row_from(self, dst_row: int, src: "DeviceIndex", src_row: int):
+        """dst row <- src row (vector, inverse norm, filter bits); the two shards may sit on different GPUs."""
+        N.check(self._lib.vs_copy_row(self._h, int(dst_row), src._h, int(src_row)))
+
+    def move_rows_from(self, src: "DeviceIndex", src_rows, dst_rows):
+        """Batched ``copy_row_from``: one kernel on this index's GPU (vs_move_rows)."""
+        a = np.ascontiguousarray(src_rows, dtype=np.int64).reshape(-1)
+        b = np.ascontiguousarray(dst_rows, dtype=np.int64).reshape(-1)
+        if a.shape != b.shape:
+            raise ValueError("src_rows and dst_rows differ in length")
+        if a.shape[0]:
+            N.check(self._lib.vs_move_rows(self._h, src._h, a.ctypes.data, b.ctypes.data, int(a.shape[0])))
+
+    def replicate_from(self, src: "DeviceIndex", dst_first: int, dst_stride: int):
+        """Row ``dst_first + l*dst_stride`` of this index <- row l of ``src`` for all its rows (NVLink peer reads)."""
+        N.check(self._lib.vs_replicate_from(self._h, src._h, int(dst_first), int(dst_stride)))
+
+    @property
+    def storage_dtype(self):
+        return np.dtype(np.uint16) if self.dtype == "bf16" else np.dtype(np.float32)
+
+    def get_raw(self, first: int, n: int) -> np.ndarray:
+        """Stored rows [first, first+n) in the storage dtype (bf16 as uint16 bit patterns): the persistence slab."""
+        out = np.empty((n, self.dim), dtype=self.storage_dtype)
+        N.check(self._lib.vs_get_raw_host(self._h, int(first), int(n), out.ctypes.data))
+        return out
+
+    def add_raw(self, stored_rows: np.ndarray) -> int:
+        """Append rows that are already in the storage dtype (chunked pinned upload, norms recomputed on device)."""
+        a = np.ascontiguousarray(stored_rows)
+        if a.dtype != self.storage_dtype or a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"expected [n,{self.dim}] rows of dtype {self.storage_dtype}, got {a.dtype} {a.shape}")
+        first = C.c_int64(-1)
+        N.check(self._lib.vs_add_raw_host(self._h, a.ctypes.data, a.shape[0], C.byref(first)))
+        return int(first.value)
+
     def set_row(self, row: int, vec):
         """Overwrite the vector of an existing row in place."""
         a = np.ascontiguousarray(vec, dtype=np.float32).reshape(-1)
@@ -138,13 +214,25 @@ class DeviceIndex:
         n = len(bits_lists)
         if n == 0:
             return
-        words = np.zeros((n, N.MASK_WORDS), dtype=np.uint64)
-        for j, bits in enumerate(bits_lists):
-            for b in bits:
-                if not 0 <= b < 64 * N.MASK_WORDS:
-                    raise ValueError(f"filter bit {b} out of range [0,{64 * N.MASK_WORDS})")
-                words[j, b // 64] |= np.uint64(1 << (b % 64))
-        N.check(self._lib.vs_set_mask_bits_range(self._h, int(first), n, words.ctypes.data))
+        self.set_filter_words_range(first, bits_to_words(bits_lists))
+
+    def set_filter_words_range(self, first: int, words: np.ndarray):
+        """Raw form: uint64 [n, MASK_WORDS] bit words of rows [first, first + n)."""
+        w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, N.MASK_WORDS)
+        if w.shape[0]:
+            N.check(self._lib.vs_set_mask_bits_range(self._h, int(first), int(w.shape[0]), w.ctypes.data))
+
+    def get_filter_words_range(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros((n, N.MASK_WORDS), dtype=np.uint64)
+        if n:
+            N.check(self._lib.vs_get_mask_bits_range(self._h, int(first), int(n), out.ctypes.data))
+        return out
+
+    def apply_sweep_bits_dev(self, words_dev, bit: int, stream=None):
+        """Filter bit ``bit`` of every row := the row's bit in one filter's sweep output (stays on the GPU)."""
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(words_dev.device)
+        N.check(self._lib.vs_apply_sweep_bits_dev(self._h, _ptr(words_dev), int(bit), _stream_ptr(st)))
 
     def get_filter_bits(self, row: int):
         w = (C.c_uint64 * N.MASK_WORDS)()
@@ -184,7 +272,7 @@ class DeviceIndex:
         return s, r
 
     def query_dev(self, q, k: int, out_scores=None, out_rows=None, require_bits: Optional[Sequence[int]] = None,
-                  mode: str = "auto", stream=None):
+                  mode: str = "auto", stream=None, pipelined: bool = False):
         """DEVICE-buffer query, asynchronous on ``stream`` (default: torch's current stream)."""
         import torch
         if q.dim() == 1:
@@ -198,8 +286,8 @@ class DeviceIndex:
         if out_rows is None:
             out_rows = torch.empty((B, k), dtype=torch.int64, device=q.device)
         st = stream if stream is not None else torch.cuda.current_stream(q.device)
-        N.check(self._lib.vs_query_topk_dev(self._h, _ptr(q), B, int(k), _bits_array(require_bits), _MODES[mode],
-                                            _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
+        N.check(self._lib.vs_query_topk_dev(self._h, _ptr(q), B, int(k), _bits_array(require_bits),
+                                            _mode(mode, pipelined), _ptr(out_scores), _ptr(out_rows), _stream_ptr(st)))
         return out_scores, out_rows
 
     def query_multimodal(self, img, txt, w, k: int, require_bits: Optional[Sequence[int]] = None,
@@ -323,7 +411,7 @@ class DeviceIndex:
         N.check(self._lib.vs_exchange_begin(self._h))
 
     def query_push_dev(self, q, k: int, slot0: int, require_bits: Optional[Sequence[int]] = None,
-                       mode: str = "auto", stream=None):
+                       mode: str = "auto", stream=None, pipelined: bool = False):
         """Local query + push of its candidates into slots [slot0, slot0+B) of every peer; no waiting."""
         import torch
         if q.dim() == 1:
@@ -333,7 +421,7 @@ class DeviceIndex:
         q = q.contiguous()
         st = stream if stream is not None else torch.cuda.current_stream(q.device)
         N.check(self._lib.vs_query_topk_push_dev(self._h, _ptr(q), q.shape[0], int(k), _bits_array(require_bits),
-                                                 _MODES[mode], int(slot0), _stream_ptr(st)))
+                                                 _mode(mode, pipelined), int(slot0), _stream_ptr(st)))
 
     def exchange_collect_dev(self, B: int, k: int, out_scores=None, out_rows=None, stream=None):
         """Wait for and merge slots [0, B) of the open exchange -> global (scores [B,k], rows [B,k])."""
@@ -349,7 +437,12 @@ class DeviceIndex:
         return out_scores, out_rows
 
     def exchange_error(self) -> int:
+        """Non-zero after a peer failed to deliver within ~3 s (the affected results came back EMPTY).
+        Reads a host-mapped word: no CUDA call, but only meaningful after the stream was synchronised."""
         return int(self._lib.vs_exchange_error(self._h))
+
+    def exchange_clear_error(self):
+        N.check(self._lib.vs_exchange_clear_error(self._h))
 
     # -- filter sweep / dedup -----------------------------------------------------------------
     def filter_words(self) -> int:
@@ -363,6 +456,21 @@ class DeviceIndex:
         out = np.zeros((a.shape[0], self.filter_words()), dtype=np.uint32)
         N.check(self._lib.vs_filter_sweep_host(self._h, a.ctypes.data, a.shape[0], float(tau), out.ctypes.data))
         return out
+
+    def apply_filter_sweep(self, prompt, tau: float, bit: int) -> int:
+        """One prompt: sweep all rows (K3) and store the outcome as filter bit ``bit`` of every row, all on
+        the GPU (the answers the reference writes one Moondream call at a time, backend/app/main.py:1010-1033).
+        Returns the number of rows that passed."""
+        import torch
+        if len(self) == 0:
+            return 0
+        dev = torch.device("cuda", self.device)
+        p = torch.from_numpy(np.ascontiguousarray(prompt, dtype=np.float32).reshape(1, self.dim)).to(dev)
+        with torch.cuda.device(dev):
+            words = self.filter_sweep_dev(p, tau)
+            self.apply_sweep_bits_dev(words, bit)
+            w = words.cpu().numpy()
+        return int(np.unpackbits(w.view(np.uint8)).sum())
 
     def filter_sweep_dev(self, prompts, tau: float, out_bits=None, stream=None):
         import torch

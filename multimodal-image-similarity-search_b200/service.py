@@ -146,18 +146,61 @@ class SearchService:
         return metadata, True
 
 
+    # -- filter sweep: process_filter_on_all_images (backend/app/main.py:939-1056) ------------------
+    def process_filter_on_all_images(self, filter_query: str, tau: float = 0.25, prompt_embedding=None) -> None:
+        """Same name, progress contract and error behaviour as the reference's background task
+        (main.py:939-1056; started from POST /api/filters at :410): the reference asks Moondream one
+        image at a time; here the filter text is CLIP-encoded ONCE and swept over every stored image
+        embedding on tensor cores (K3); rows with ``cos >= tau`` answer "yes".  The outcome lands where the
+        post-filter (main.py:215) and the pre-filter kernels read it (``Collection.apply_filter_sweep``).
+        Progress: ``get_filter_progress`` / ``collection.filter_progress`` (GET /api/filter-progress)."""
+        try:
+            if prompt_embedding is None:
+                if self.encoder is None:
+                    logger.error("CLIP encoder not available, cannot process filter")
+                    self.collection.filter_progress[filter_query] = {"status": "error", "message": "Model not available",
+                                                                     "progress": 0}
+                    return
+                prompt_embedding = self.encoder(text=filter_query)["text"][0]
+            self.collection.apply_filter_sweep(filter_query, prompt_embedding, tau)
+        except Exception as e:       # the reference records the error and returns (main.py:1049-1056)
+            logger.error("Error processing filter on all images: %s", e)
+            self.collection.filter_progress[filter_query] = {"status": "error", "message": str(e), "progress": 0}
+
+    def get_filter_progress(self, filter_query: str) -> Dict[str, Any]:
+        """Body of GET /api/filter-progress (main.py:1100-1108)."""
+        progress = getattr(self.collection, "filter_progress", {})
+        if filter_query not in progress:
+            return {"status": "not_found"}
+        return progress[filter_query]
+
+    # -- reset_system (backend/app/main.py:1058-1098): delete every id in ONE call ----------------------
+    def reset_system(self) -> bool:
+        try:
+            all_ids = self.collection.get(include=[])["ids"]
+            if all_ids:
+                self.collection.delete(ids=all_ids)
+            return True
+        except Exception as e:
+            logger.error("Error during system reset: %s", e)
+            return False
+
+
 class MicroBatcher:
     """Server-side micro-batching of concurrent single queries: the
     reference answers one request at a time (`search_similar`, backend/app/main.py:748-805, called
     inline from the async routes); under load the requests that arrive within ``max_wait_ms`` of each
     other are stacked into ONE ``collection.query`` so the batched tcgen05 kernel (K2) serves them in
-    a single pass over the corpus.  Each caller gets exactly what its own
-    ``collection.query(query_embeddings=[e], n_results=n, include=...)`` would have returned."""
+    a single pass over the corpus.  ``mode="scan"`` (default) keeps every caller's answer bit-identical to
+    its own ``collection.query(query_embeddings=[e], n_results=n, include=...)``; ``mode="auto"`` lets
+    batches of >= 16 queries on a bf16 collection take the tensor path, whose queries are rounded to
+    bf16: scores then agree within the bf16 tolerance (2e-3) and near-ties may order differently."""
 
     def __init__(self, collection, max_batch: int = 64, max_wait_ms: float = 2.0,
-                 include: Sequence[str] = ("metadatas", "distances")):
+                 include: Sequence[str] = ("metadatas", "distances"), mode: str = "scan"):
         import threading
         self.collection, self.max_batch, self.max_wait = collection, int(max_batch), max_wait_ms / 1e3
+        self.mode = mode
         self.include = list(include)
         self._cv = threading.Condition()
         self._pending: List[Dict[str, Any]] = []
@@ -199,7 +242,7 @@ class MicroBatcher:
             try:
                 n_max = max(r["n"] for r in batch)
                 res = self.collection.query(query_embeddings=np.stack([r["e"] for r in batch]), n_results=n_max,
-                                            include=self.include)
+                                            include=self.include, mode=self.mode)
                 self.batches.append(len(batch))
                 for b, r in enumerate(batch):
                     one = dict(res)

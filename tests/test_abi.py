@@ -24,7 +24,7 @@ def _declared_symbols():
 def test_library_is_built_in_tree_and_loads():
     assert os.path.dirname(N.LIB_PATH) == os.path.join(ROOT, "multimodal-image-similarity-search_b200")
     lib = mmiss_b200.load_native()
-    assert lib.vs_abi_version() == 1
+    assert lib.vs_abi_version() == 2
     assert lib.vs_launch_count() >= 0
 
 
