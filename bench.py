@@ -5,28 +5,36 @@
     python bench.py --impl reference [...]                         # reference arm (CPU exact path)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # N ranks, one GPU each
 
-A *step* is one batch of Q independent single queries over the whole corpus: every query is its
-own fused scan kernel launch that streams the rank's shard from HBM once (K1).  With N > 1 the LAST
-CTA of that same kernel stores the shard's k candidates into every peer's exchange buffer over
-NVLink (P2P stores + flags) and merges the N lists, so every rank ends with the global top-k and
-the query is still ONE kernel, no NCCL call (--exchange nccl: all-gather + merge kernel K5).  The
-corpus (10M rows total, row-sharded ceil(N/G) per rank => "strong" scaling) is resident in HBM
-before the timed region; it is >> L2 (126 MB), so no flush is needed between iterations.
+A *step* is one batch of Q = 32*N independent single queries over the whole corpus (N = number of GPUs, so
+a step lasts ~45 ms at every N): every query is its own fused scan kernel launch that streams the rank's
+shard from HBM once (K1).  With N > 1 the LAST CTA of that same kernel stores the shard's k candidates into
+every peer's exchange buffer over NVLink (P2P stores + flags); one collect kernel per step merges the N
+lists, so every rank ends with the global top-k and there is no NCCL call on the query path (--exchange
+nccl: all-gather + merge kernel K5).  The corpus (10M rows total, row-sharded ceil(N/G) per rank => "strong"
+scaling) is resident in HBM before the timed region; it is >> L2 (126 MB), so no flush is needed.
 
-`value`   = queries/s over all ranks, device-timed (CUDA events, max over ranks).
-`e2e`     = same metric through the host-buffer API: per step ONE H2D of the step's queries from pinned
-            memory, the Q single-query scans (+ exchange when N>1), D2H of the [Q, k] result, sync;
-            `e2e.per_query_sync` = the same with copy + sync per query (one request at a time).
+`value`   = queries/s over all ranks, device-timed (CUDA events, max over ranks): `--blocks` timed blocks of
+            EXACTLY K steps each, the MEDIAN block is reported (all blocks in `blocks_ms`).
+`parity_check` = (outside the timed region) near-duplicates of the parity queries are planted at known GLOBAL
+            rows on known shards, incl. an exact cross-shard tie; every rank asserts rank order and scores,
+            and the NCCL arm must reproduce the fused-exchange result bit for bit.
+`e2e`     = same metric through the host-buffer API: per step the queries leave pinned host memory on rank 0
+            (N>1: H2D + broadcast to the other ranks = the front end's fan-out), Q single-query scans
+            (+ exchange), D2H of the [Q, k] result, sync.
+`e2e_per_query` = ONE request at a time (the reference's service shape, backend/app/main.py:748-805) through
+            the single-process group `vs_group_query_host` spanning all N GPUs: no torchrun, no stream sync.
 `roofline`= the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-`cpu_baseline` = the oracle port of the reference's exact path (numpy matmul + top-k) on this
-            box's host cores, on a bounded row sample, scaled to the full corpus.
+`cpu_baseline` = the oracle port of the reference's exact path (numpy matmul + top-k) on this box's host
+            cores: the full 10M x 512 corpus when host RAM allows, else a row sample scaled.
+Extras (not the headline): BASELINE configs 2 (1M x 512 f32), 3 (B=1024 blended queries, tcgen05), 4 (filter
+sweep) and 5 (2M x 768 all-pairs dedup, triangle split over the ranks).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
+import statistics
 import sys
 import time
 
@@ -44,20 +52,13 @@ HBM_FALLBACK_GBS = 6650.0
 
 def ncu_traffic_bytes(rows_local: int, dim: int, dtype: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per scan launch from the committed `ncu --set full`
-    capture (profiles/r01c_ncu_scan_topk.txt, first launch; taken on 10M x 512 bf16); None for any other shape."""
-    if (rows_local, dim, dtype) != (10_000_000, 512, "bf16"):
-        return None
+    captures (profiles/ncu_scan_traffic.json: "rows x dim dtype" -> bytes, with the source file); None for
+    a shape that was never captured."""
     try:
-        total = 0.0
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        seen = set()
-        for ln in open(os.path.join(ROOT, "profiles", "r01c_ncu_scan_topk.txt")):
-            key = ln.split("=")[0].strip()
-            if key in ("dram__bytes_read.sum", "dram__bytes_write.sum") and key not in seen:
-                seen.add(key)
-                val, unit = ln.split("=")[1].split()
-                total += float(val) * scale[unit]
-        return total or None
+        with open(os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")) as f:
+            table = json.load(f)
+        ent = table.get(f"{rows_local}x{dim} {dtype}")
+        return float(ent["bytes"]) if ent else None
     except Exception:
         return None
 
@@ -70,12 +71,25 @@ def measured_peaks():
     return {"hbm_gbs": HBM_FALLBACK_GBS, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def queries_per_step(args, G):
+    return args.queries * G
+
+
+def workload_config(args, G):
+    Q = queries_per_step(args, G)
+    return {"workload": f"{args.rows}x{args.dim} {args.dtype} unit-norm corpus, exact top-{args.k} cosine, "
+                        f"{Q} single-query scans per step",
+            "rows_total": args.rows, "rows_per_gpu": (args.rows + G - 1) // G, "dim": args.dim, "k": args.k,
+            "queries_per_step": Q, "parallelism": f"row-shard x{G}",
+            "l2": "inputs larger than L2 (no flush needed)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's exact path (numpy `X @ q` + argpartition),
-# restated in oracle/cosine_oracle.py; timed on a bounded sample.
+# restated in oracle/cosine_oracle.py.
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_qps(total_rows: int, dim: int, k: int, budget_s: float, sample_rows: int = 1_000_000,
-                      min_queries: int = 3):
+                      min_queries: int = 3, try_full: bool = True):
     from oracle import cosine_oracle as O
     # all the host threads BLAS can use, also under torchrun (which exports OMP_NUM_THREADS=1)
     ncores = int(os.cpu_count() or 1)
@@ -89,34 +103,57 @@ def cpu_reference_qps(total_rows: int, dim: int, k: int, budget_s: float, sample
     rng = np.random.default_rng(0)
     sample_rows = min(sample_rows, total_rows)
     X = O.bf16_round(O.normalize_rows(rng.standard_normal((sample_rows, dim), dtype=np.float32)))
-    inv = O.inv_norms(X)
     Q = O.normalize_rows(rng.standard_normal((64, dim), dtype=np.float32))
 
-    def one(q):
-        s = (X @ q) * inv                      # the scan
-        idx = np.argpartition(-s, k)[:k]       # top-k
-        return idx[np.argsort(-s[idx], kind="stable")]
+    def timed(Xm, inv, budget):
+        def one(q):
+            s = (Xm @ q) * inv                     # the scan
+            idx = np.argpartition(-s, k)[:k]       # top-k
+            return idx[np.argsort(-s[idx], kind="stable")]
+        one(Q[0])                                  # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            one(Q[n % 64])
+            n += 1
+            dt = time.perf_counter() - t0
+            if (dt >= budget and n >= min_queries) or n >= 4096:
+                return n, dt
 
-    one(Q[0])                                  # warm-up
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        one(Q[n % 64])
-        n += 1
-        dt = time.perf_counter() - t0
-        if (dt >= budget_s and n >= min_queries) or n >= 4096:
-            break
-    qps_sample = n / dt
+    full = None
+    try:
+        import psutil
+        need = total_rows * dim * 4 * 1.35
+        if try_full and total_rows > sample_rows and psutil.virtual_memory().available > need + (8 << 30):
+            # fp32 view of the whole bf16 corpus: tiled from the sample block with a
+            # per-block sign (content does not change the cost of a dense scan)
+            Xf = np.empty((total_rows, dim), dtype=np.float32)
+            for b0 in range(0, total_rows, sample_rows):
+                m = min(sample_rows, total_rows - b0)
+                np.multiply(X[:m], 1.0 if (b0 // sample_rows) % 2 == 0 else -1.0, out=Xf[b0:b0 + m])
+            invf = np.ones(total_rows, dtype=np.float32)
+            n, dt = timed(Xf, invf, budget_s * 0.6)
+            full = {"qps": n / dt, "queries": n, "seconds": dt}
+            del Xf, invf
+    except Exception as e:                            # noqa: BLE001 -- fall back to the sample
+        full = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+    n, dt = timed(X, O.inv_norms(X), budget_s * (0.4 if full and "qps" in full else 1.0))
+    scaled = (n / dt) * sample_rows / total_rows
     if _limit is not None:
         _limit.restore_original_limits()
+    use_full = bool(full and "qps" in full)
     return {
-        "value": qps_sample * sample_rows / total_rows,
+        "value": full["qps"] if use_full else scaled,
         "unit": "queries/s",
-        "cores": int(os.cpu_count() or 1),
+        "cores": ncores,
         "threads": int(threads),
         "kind": "port",
-        "sample": f"{n} single queries over a {sample_rows}x{dim} row sample (fp32 view of the bf16 corpus, numpy "
-                  f"matmul+argpartition, {dt:.1f}s), QPS scaled by {sample_rows}/{total_rows} rows",
+        "sample": (f"{full['queries']} single queries over the FULL {total_rows}x{dim} corpus (fp32 view, numpy matmul+"
+                   f"argpartition, {full['seconds']:.1f}s)" if use_full else
+                   f"{n} single queries over a {sample_rows}x{dim} row sample (fp32 view of the bf16 corpus, numpy "
+                   f"matmul+argpartition, {dt:.1f}s), QPS scaled by {sample_rows}/{total_rows} rows"),
+        "extrapolated_from_sample": {"value": scaled, "sample_rows": sample_rows, "queries": n, "seconds": dt},
+        "full_corpus": full,
     }
 
 
@@ -138,12 +175,13 @@ def run_reference(args):
                     hnsw_oracle.measure(args.hnsw_rows, args.dim, 200, args.k, clustered=False)]
         except Exception as e:                        # noqa: BLE001 -- gcc missing etc.: report, do not fail the arm
             hnsw = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    Q = queries_per_step(args, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * Q / base["value"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall, "hnsw_recall_vs_exact": hnsw,
@@ -151,14 +189,6 @@ def run_reference(args):
                 "(numpy matmul + top-k) as restated in oracle/, all host threads BLAS uses",
     }
     print(json.dumps(line))
-
-
-def workload_config(args, G):
-    return {"workload": f"{args.rows}x{args.dim} {args.dtype} unit-norm corpus, exact top-{args.k} cosine, "
-                        f"{args.queries} single-query scans per step",
-            "rows_total": args.rows, "rows_per_gpu": (args.rows + G - 1) // G, "dim": args.dim, "k": args.k,
-            "queries_per_step": args.queries, "parallelism": f"row-shard x{G}",
-            "l2": "inputs larger than L2 (no flush needed)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,6 +245,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# parity plants: near-duplicates of the parity queries at known GLOBAL rows
+# ------------------------------------------------------------------------------------------------
+PARITY_QUERIES = 8
+PLANT_EPS = (0.05, 0.15, 0.30, 0.50)      # cos ~ 0.9988, 0.989, 0.958, 0.894 (random 512-d rows: |cos| < 0.25)
+TIE_EPS = 0.40                            # two rows with the SAME vector (cos ~ 0.928) on the first and last shard
+
+
+def parity_plan(n_rows: int, dim: int):
+    """queries [P, dim] + for each query the planted (global row, vector) pairs in expected rank order."""
+    rng = np.random.default_rng(20260)
+    q = rng.standard_normal((PARITY_QUERIES, dim)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    plants = []
+    for j in range(PARITY_QUERIES):
+        rows, vecs = [], []
+        for m, eps in enumerate(PLANT_EPS):
+            g = ((2 * (j * len(PLANT_EPS) + m) + 1) * n_rows) // (2 * PARITY_QUERIES * len(PLANT_EPS))   # spread over all shards
+            noise = rng.standard_normal(dim).astype(np.float32)
+            noise /= np.linalg.norm(noise)
+            v = q[j] + eps * noise
+            rows.append(int(g)); vecs.append(v / np.linalg.norm(v))
+        noise = rng.standard_normal(dim).astype(np.float32)
+        noise /= np.linalg.norm(noise)
+        v = q[j] + TIE_EPS * noise
+        v /= np.linalg.norm(v)
+        tie_rows = [1000 + j, n_rows - 1000 - j]           # first shard / last shard (striped: both parities)
+        order = sorted(zip([*rows, *tie_rows], [*vecs, v, v]), key=lambda t: (-float(np.dot(q[j], t[1])), t[0]))
+        plants.append(order)
+    return q, plants
+
+
+def expected_scores(q, plants, dtype):
+    from oracle import cosine_oracle as O
+    out = []
+    for j, order in enumerate(plants):
+        V = np.stack([v for _, v in order])
+        Vs = O.bf16_round(V) if dtype == "bf16" else V
+        s = (Vs.astype(np.float64) @ q[j].astype(np.float64)) / np.linalg.norm(Vs.astype(np.float64), axis=1)
+        out.append(s)
+    return out
+
+
+def check_planted(rows, scores, plants, want_scores, tol):
+    """rows/scores [P, k] numpy of the GLOBAL result -> (ok, first problem)."""
+    for j, order in enumerate(plants):
+        want_rows = [g for g, _ in order]
+        got = rows[j][:len(want_rows)].tolist()
+        if got != want_rows:
+            return False, f"query {j}: rows {got} != planted {want_rows}"
+        err = np.abs(scores[j][:len(want_rows)].astype(np.float64) - want_scores[j]).max()
+        if err > tol:
+            return False, f"query {j}: score error {err:.2e} > {tol}"
+    return True, ""
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -229,36 +315,48 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")       # host-side barriers that keep the GPUs idle
     G = world
     lo, hi = M.shard_bounds(args.rows, G, rank)
     n_local = hi - lo
+    tol = 2e-3 if args.dtype == "bf16" else 1e-5
+    chunk = 1 << 19
+    gen = torch.Generator(device=dev)
+
+    def corpus_chunk(c0, n, dim, seed=1234, device=dev, g=gen):
+        g.manual_seed(seed + c0)                  # chunk content depends only on its global offset
+        x = torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
+        return torch.nn.functional.normalize(x, dim=1)
 
     # ---- build the shard (synthetic unit-norm rows, generated on the device in chunks) --------
     ix = M.DeviceIndex(args.dim, args.dtype, device=local_rank, capacity=n_local, row_base=lo)
-    chunk = 1 << 19
-    gen = torch.Generator(device=dev)
     t_build = time.perf_counter()
     for c0 in range(lo, hi, chunk):
-        n = min(chunk, hi - c0)
-        gen.manual_seed(1234 + c0)               # chunk content depends only on its global offset
-        x = torch.randn((n, args.dim), generator=gen, device=dev, dtype=torch.float32)
-        x = torch.nn.functional.normalize(x, dim=1)
-        ix.add(x)
+        ix.add(corpus_chunk(c0, min(chunk, hi - c0), args.dim))
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     assert len(ix) == n_local
-    del x
 
-    Q = args.queries
+    # ---- parity plants (before anything is timed) ----------------------------------------------
+    pq, plants = parity_plan(args.rows, args.dim)
+    want_scores = expected_scores(pq, plants, args.dtype)
+    for order in plants:
+        for g_row, v in order:
+            if lo <= g_row < hi:
+                ix.set_row(g_row - lo, v)
+
+    Q = queries_per_step(args, G)
     gq = torch.Generator(device="cpu").manual_seed(99)
     q_host = torch.nn.functional.normalize(torch.randn((Q, args.dim), generator=gq), dim=1).pin_memory()
+    q_host[:PARITY_QUERIES] = torch.from_numpy(pq)          # the step's first queries are the parity queries
     q_dev = q_host.to(dev)
     k = args.k
     cand_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
     cand_r = torch.empty((Q, k), dtype=torch.int64, device=dev)
-    searcher, exchange = None, "none"
+    searcher, nccl_searcher, exchange = None, None, "none"
     if G > 1:
         exchange = args.exchange
         if exchange == "p2p":
@@ -273,8 +371,9 @@ def run_ours(args):
                 if searcher is not None:
                     exchange = "nccl (p2p unavailable on a peer)"
                 searcher = None
+        nccl_searcher = M.ShardedSearcher.for_index(ix, mode="scan", exchange="nccl")
         if searcher is None:
-            searcher = M.ShardedSearcher.for_index(ix, mode="scan", exchange="nccl")
+            searcher = nccl_searcher
     p2p = searcher is not None and searcher.exchange == "p2p"
     gath_s = torch.empty((G, Q, k), dtype=torch.float32, device=dev) if G > 1 else None
     gath_r = torch.empty((G, Q, k), dtype=torch.int64, device=dev) if G > 1 else None
@@ -286,13 +385,15 @@ def run_ours(args):
         if timed:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
+        # q_dev was complete long before the first launch: VS_Q_PIPELINED lets query i+1 stream while query i merges
         if p2p:        # every scan kernel pushes its top-k to all peers over NVLink; one collect kernel per step
             ix.exchange_begin()
             for i in range(Q):
-                ix.query_push_dev(q_dev[i:i + 1], k, i, mode="scan")
+                ix.query_push_dev(q_dev[i:i + 1], k, i, mode="scan", pipelined=True)
         else:
             for i in range(Q):                   # Q independent single-query scans (one kernel each)
-                ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan")
+                ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan",
+                             pipelined=True)
         if timed:
             e1.record()
             scan_ev.append((e0, e1))
@@ -313,54 +414,67 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         res_s, res_r = step(False)
     barrier()
+
+    # ---- parity check of exactly the path that is timed (and of the NCCL arm) --------------------
+    ok, why = check_planted(res_r[:PARITY_QUERIES].cpu().numpy(), res_s[:PARITY_QUERIES].cpu().numpy(), plants, want_scores, tol)
+    eq_nccl = None
+    if G > 1:
+        s2, r2 = nccl_searcher.search(q_dev[:PARITY_QUERIES], k)
+        torch.cuda.synchronize()
+        if p2p:
+            eq_nccl = bool(torch.equal(r2, res_r[:PARITY_QUERIES]) and torch.equal(s2, res_s[:PARITY_QUERIES]))
+        ok2, why2 = check_planted(r2.cpu().numpy(), s2.cpu().numpy(), plants, want_scores, tol)
+        ok, why = ok and ok2, why or why2
+        if p2p and ix.exchange_error():
+            ok, why = False, "peer exchange timed out"
+    flags = torch.tensor([1 if ok else 0, 1 if eq_nccl in (None, True) else 0], device=dev)
+    if G > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    parity = {"queries": PARITY_QUERIES, "planted_rows_per_query": len(PLANT_EPS) + 2, "cross_shard_tie": True,
+              "ranks_checked": G, "planted_ok": bool(flags[0].item()), "tolerance": tol,
+              "p2p_eq_nccl": (bool(flags[1].item()) if (G > 1 and p2p) else None),
+              "first_problem_rank0": why or None}
+    if not parity["planted_ok"] or parity["p2p_eq_nccl"] is False:
+        raise SystemExit(f"bench.py: parity check FAILED on rank {rank}: {why} (p2p_eq_nccl={eq_nccl})")
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = M.launch_count()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        res_s, res_r = step(True)
-    t1.record()
-    barrier()
-    elapsed_ms = t0.elapsed_time(t1)
-    launches = M.launch_count() - launches0
+    blocks_ms = []
+    for _ in range(max(1, args.blocks)):
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for _ in range(args.steps):
+            res_s, res_r = step(True)
+        t1.record()
+        barrier()
+        blocks_ms.append(t0.elapsed_time(t1))
+    launches = (M.launch_count() - launches0) // max(1, args.blocks)
     clocks = sampler.stop() if sampler else None
     scan_ms = sum(a.elapsed_time(b) for a, b in scan_ev) / (len(scan_ev) * Q)
-
-    # ---- correctness spot-check of the timed result (first 2 queries vs torch fp32 on this shard
-    #      is not possible globally without the full corpus; check local candidates instead) ----
     rows_bytes = n_local * (args.dim * (2 if args.dtype == "bf16" else 4) + 4)
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------
-    # (a) per step (the contract's definition): the step's Q queries go host->device in ONE copy from
-    #     pinned memory, are scored by Q independent single-query scans (one launch, grid.y = Q: every
-    #     query still streams the whole shard by itself), and the [Q, k] result is read back.
-    # (b) per query (a search service answering one request at a time): copy, scan, read back, sync.
+    # per step: the step's Q queries leave pinned host memory on rank 0 in ONE copy, reach every rank (N>1: NCCL
+    # broadcast = the front end's fan-out), are scored by Q single-query scans (one launch, grid.y = Q: every query
+    # still streams the whole shard by itself), and the [Q, k] result is read back on rank 0.
     e2e_steps = max(1, min(args.steps, 5))
     h_out_s = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     h_out_r = torch.empty((Q, k), dtype=torch.int64).pin_memory()
     q_np = q_host.numpy()
+    qd_e2e = torch.empty((Q, args.dim), dtype=torch.float32, device=dev)
 
     def e2e_step():
         if G == 1:
             return ix.query(q_np, k, mode="scan")                 # vs_query_topk_host: H2D + Q scans + D2H + sync
-        qd = q_host.to(dev, non_blocking=True)                    # H2D from pinned memory
-        s, r = searcher.search(qd, k)                             # Q scans + exchange (+ merge)
-        h_out_s.copy_(s, non_blocking=True); h_out_r.copy_(r, non_blocking=True)
+        if rank == 0:
+            qd_e2e.copy_(q_host, non_blocking=True)               # H2D from pinned memory on the front-end rank
+        dist.broadcast(qd_e2e, src=0)                             # fan-out over NVLink
+        s, r = searcher.search(qd_e2e, k)                         # Q scans + exchange (+ merge)
+        if rank == 0:
+            h_out_s.copy_(s, non_blocking=True); h_out_r.copy_(r, non_blocking=True)
         torch.cuda.synchronize()
         return h_out_s, h_out_r
-
-    def e2e_query_step():
-        for i in range(Q):
-            if G == 1:
-                ix.query(q_np[i:i + 1], k, mode="scan")
-            elif p2p:
-                ix.query_sharded(q_np[i:i + 1], k, mode="scan")   # vs_query_topk_sharded_host: H2D + kernel/exchange + D2H + sync
-            else:
-                qd = q_host[i:i + 1].to(dev, non_blocking=True)
-                s, r = searcher.search(qd, k)
-                h_out_s[i:i + 1].copy_(s, non_blocking=True); h_out_r[i:i + 1].copy_(r, non_blocking=True)
-                torch.cuda.synchronize()
 
     def wall(fn, reps):
         fn()
@@ -372,10 +486,10 @@ def run_ours(args):
         return time.perf_counter() - w0
 
     e2e_res = e2e_step()
-    # the timed device result and the host-API result of the same queries must agree
-    assert np.array_equal(np.asarray(e2e_res[1]), res_r.cpu().numpy()), "e2e result differs from the device-timed result"
+    if rank == 0:
+        # the timed device result and the host-API result of the same queries must agree
+        assert np.array_equal(np.asarray(e2e_res[1]), res_r.cpu().numpy()), "e2e result differs from the device-timed result"
     e2e_s = wall(e2e_step, e2e_steps)
-    e2e_q_s = wall(e2e_query_step, e2e_steps)
 
     # ---- extra (not the headline): BASELINE config 3, B blended text+image queries on tcgen05 --------
     batched_ms = 0.0
@@ -415,8 +529,8 @@ def run_ours(args):
         barrier()
         batched_ms = b0.elapsed_time(b1) / 5
 
-    # ---- extras (not the headline): BASELINE configs 4 and 5 on this rank's shard -------------------------
-    filter_ms, dedup_ms, dedup_rows, dedup_dim = 0.0, 0.0, 0, 768
+    # ---- extra: BASELINE config 4 (filter sweep) on this rank's shard -------------------------------
+    filter_ms = 0.0
     if args.dtype == "bf16" and args.filters > 0:
         gf = torch.Generator(device=dev).manual_seed(4343)
         prompts = torch.randn((args.filters, args.dim), generator=gf, device=dev)
@@ -432,38 +546,119 @@ def run_ours(args):
         barrier()
         filter_ms = f0.elapsed_time(f1) / 5
         del fbits
-    if args.dtype == "bf16" and args.dedup_rows > 0 and G == 1:
-        dedup_rows = args.dedup_rows
-        dx = M.DeviceIndex(dedup_dim, "bf16", device=local_rank, capacity=dedup_rows)
-        for c0 in range(0, dedup_rows, chunk):
-            n = min(chunk, dedup_rows - c0)
-            gen.manual_seed(777 + c0)
-            dx.add(torch.nn.functional.normalize(torch.randn((n, dedup_dim), generator=gen, device=dev), dim=1))
-        cap = 1 << 16
+
+    # ---- extra: BASELINE config 2 (1M x 512 fp32, single-query scans) on one GPU ---------------------
+    f32_info = None
+    if G == 1 and args.f32_rows > 0:
+        fx = M.DeviceIndex(args.dim, "f32", device=local_rank, capacity=args.f32_rows)
+        for c0 in range(0, args.f32_rows, chunk):
+            fx.add(corpus_chunk(c0, min(chunk, args.f32_rows - c0), args.dim, seed=555))
+        fs = torch.empty((1, k), dtype=torch.float32, device=dev); fr = torch.empty((1, k), dtype=torch.int64, device=dev)
+        nq = 100
+        gq2 = torch.Generator(device=dev).manual_seed(1)
+        fq = torch.nn.functional.normalize(torch.randn((nq, args.dim), generator=gq2, device=dev), dim=1)
+        for i in range(10):
+            fx.query_dev(fq[i:i + 1], k, out_scores=fs, out_rows=fr, mode="scan", pipelined=True)
+        torch.cuda.synchronize()
+        c0e = torch.cuda.Event(enable_timing=True); c1e = torch.cuda.Event(enable_timing=True)
+        c0e.record()
+        for rep in range(3):
+            for i in range(nq):
+                fx.query_dev(fq[i:i + 1], k, out_scores=fs, out_rows=fr, mode="scan", pipelined=True)
+        c1e.record()
+        torch.cuda.synchronize()
+        ms = c0e.elapsed_time(c1e) / (3 * nq)
+        fbytes = args.f32_rows * (args.dim * 4 + 4)
+        peaks_, _ = measured_peaks()
+        f32_info = {"workload": f"{args.f32_rows}x{args.dim} f32 unit-norm corpus, {nq} single-query exact top-{k} scans (BASELINE config 2)",
+                    "ms_per_query": ms, "qps": 1e3 / ms,
+                    "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel<float>", "achieved": fbytes / (ms / 1e3) / 1e9,
+                                 "peak": peaks_["hbm_gbs"], "unit": "GB/s", "frac": fbytes / (ms / 1e3) / 1e9 / peaks_["hbm_gbs"],
+                                 "bytes_per_launch": fbytes, "traffic": ncu_traffic_bytes(args.f32_rows, args.dim, "f32")}}
+        fx.close()
+
+    # ---- extra: BASELINE config 5 (2M x 768 all-pairs dedup; N>1: triangle split over the ranks) -----
+    dedup_info, dedup_dim = None, 768
+    if args.dtype == "bf16" and args.dedup_rows > 0:
+        nd = args.dedup_rows
+        n_plant = max(1, nd // 100)                                       # 1 % planted near-duplicates
+        assert 8 * n_plant + 3 <= nd
+        dlo, dhi = M.shard_bounds(nd, G, rank)
+        dsh = M.DeviceIndex(dedup_dim, "bf16", device=local_rank, capacity=dhi - dlo, row_base=dlo)
+        # source row 7j+3 := U[j], planted row nd-n_plant+j := normalise(U[j] + 0.1*g/sqrt(D)) (cos ~ 0.995); U and the
+        # noise are generated with one seed and one shape on every rank, so all ranks agree on them
+        gp = torch.Generator(device=dev).manual_seed(999)
+        U = torch.nn.functional.normalize(torch.randn((n_plant, dedup_dim), generator=gp, device=dev), dim=1)
+        P = torch.nn.functional.normalize(U + torch.randn((n_plant, dedup_dim), generator=gp, device=dev) * (0.1 / dedup_dim ** 0.5), dim=1)
+        for c0 in range(dlo, dhi, chunk):
+            n = min(chunk, dhi - c0)
+            x = corpus_chunk(c0, n, dedup_dim, seed=777)
+            g_idx = torch.arange(c0, c0 + n, device=dev)
+            is_src = (g_idx % 7 == 3) & (g_idx < 7 * n_plant)
+            x[is_src] = U[(g_idx[is_src] - 3) // 7]
+            is_plant = g_idx >= nd - n_plant
+            x[is_plant] = P[g_idx[is_plant] - (nd - n_plant)]
+            dsh.add(x)
+        del U, P
+        t_rep = time.perf_counter()
+        full_ix = M.replicate_index(dsh, nd) if G > 1 else dsh            # every rank needs every column
+        torch.cuda.synchronize()
+        t_rep = time.perf_counter() - t_rep
+        tlo, thi = M.triangle_bounds(nd, G, rank) if G > 1 else (0, nd)
+        cap = 1 << 17
         oi = torch.empty(cap, dtype=torch.int64, device=dev); oj = torch.empty(cap, dtype=torch.int64, device=dev)
         osc = torch.empty(cap, dtype=torch.float32, device=dev); cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-        dx.dedup_dev(0.95, 0, dedup_rows, oi, oj, osc, cnt)
-        torch.cuda.synchronize()
+        full_ix.dedup_dev(0.95, tlo, thi, oi, oj, osc, cnt)               # warm-up pass
+        barrier()
         d0 = torch.cuda.Event(enable_timing=True); d1 = torch.cuda.Event(enable_timing=True)
         d0.record()
-        for _ in range(2):
-            dx.dedup_dev(0.95, 0, dedup_rows, oi, oj, osc, cnt)
+        full_ix.dedup_dev(0.95, tlo, thi, oi, oj, osc, cnt)
         d1.record()
-        torch.cuda.synchronize()
-        dedup_ms = d0.elapsed_time(d1) / 2
-        dx.close()
+        barrier()
+        dd_ms = d0.elapsed_time(d1)
+        found = torch.tensor([int(cnt[0].item())], device=dev)
+        if G > 1:
+            dist.all_reduce(found)
+        m = min(int(cnt[0].item()), cap)
+        pairs_ok = bool((oj[:m] - oi[:m] > 0).all().item()) if m else True
+        dedup_info = {"ms": dd_ms, "rows": nd, "pairs_found": int(found.item()), "pairs_planted": n_plant,
+                      "count_ok": int(found.item()) == n_plant and pairs_ok, "replicate_s": t_rep}
+        if full_ix is not dsh:
+            full_ix.close()
+        dsh.close()
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------------
     xerr = ix.exchange_error() if p2p else 0
     if xerr:
         raise SystemExit(f"bench.py: peer exchange timed out on rank {rank} (results invalid)")
-    tvals = torch.tensor([elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s, filter_ms], dtype=torch.float64, device=dev)
+    tvals = torch.tensor([*blocks_ms, scan_ms, e2e_s, batched_ms, filter_ms, dedup_info["ms"] if dedup_info else 0.0],
+                         dtype=torch.float64, device=dev)
     if G > 1:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
-    elapsed_ms, scan_ms, e2e_s, batched_ms, e2e_q_s, filter_ms = tvals.tolist()
+    tl = tvals.tolist()
+    nb = len(blocks_ms)
+    blocks_ms, (scan_ms, e2e_s, batched_ms, filter_ms, dedup_ms) = tl[:nb], tl[nb:]
+    ix_closed = False
+
+    # ---- one request at a time through the single-process group spanning all N GPUs (rank 0 only) -----------
+    per_query = None
+    if args.group_queries > 0:
+        if G > 1:
+            ix.close()                               # free the shards; the other ranks idle on a HOST barrier
+            ix_closed = True
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                per_query = group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, tol)
+            except Exception as e:                    # noqa: BLE001 -- report, keep the headline
+                per_query = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if G > 1:
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
+        elapsed_ms = statistics.median(blocks_ms)
         qps = Q * args.steps / (elapsed_ms / 1e3)
         achieved = rows_bytes / (scan_ms / 1e3) / 1e9
         line = {
@@ -471,23 +666,24 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, G),
+            "blocks_ms": blocks_ms, "timed_region_s": elapsed_ms / 1e3,
             "scanned_gb_per_s": qps * args.rows * args.dim * (2 if args.dtype == "bf16" else 4) / 1e9,
+            "parity_check": parity,
             "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "peak_kind": peaks_kind, "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": ncu_traffic_bytes(n_local, args.dim, args.dtype),
                          "bytes_per_launch": rows_bytes, "avg_launch_ms": scan_ms,
                          "note": "peak = MEASURED_PEAKS.json hbm_gbs, a read+write COPY bandwidth; this kernel only "
-                                 "reads, so frac can exceed 1 (ncu: gpu__dram_throughput 88.8 % of the DRAM peak, "
-                                 "profiles/r01c_ncu_scan_topk.txt); avg_launch_ms is per scan inside a burst of "
-                                 "back-to-back launches (consecutive scans overlap under PDL)"},
+                                 "reads, so frac can exceed 1 (ncu: gpu__dram_throughput ~89 % of the DRAM peak, "
+                                 "profiles/); avg_launch_ms is per scan inside a burst of back-to-back launches "
+                                 "(consecutive scans overlap under PDL)"},
             "e2e": {"value": Q * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q * args.dim * 4,
                     "d2h_bytes_per_step": Q * k * 12, "steps": e2e_steps,
                     "path": ("vs_query_topk_host(B=%d, scan) via ctypes" % Q) if G == 1 else
-                    f"ShardedSearcher.search ({'scan + fused p2p exchange' if p2p else 'scan + nccl all-gather + merge'}) "
-                    "+ pinned H2D/D2H",
-                    "per_query_sync": {"value": Q * e2e_steps / e2e_q_s, "unit": "queries/s",
-                                       "note": "one request at a time: H2D, scan, D2H, sync per query"}},
+                    f"pinned H2D on rank 0 + NCCL broadcast of the queries + ShardedSearcher.search "
+                    f"({'scan + fused p2p exchange' if p2p else 'scan + nccl all-gather + merge'}) + D2H on rank 0"},
+            "e2e_per_query": per_query,
             "gpu_launches": int(launches), "clocks": clocks, "build_s": t_build, "exchange": exchange,
         }
         if batched_ms > 0:
@@ -506,18 +702,89 @@ def run_ours(args):
                                     "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"],
                                     "gb_per_s": fbytes / (filter_ms / 1e3) / 1e9,
                                     "frac_of_hbm": fbytes / (filter_ms / 1e3) / 1e9 / G / peaks["hbm_gbs"]}
-        if dedup_ms > 0:
-            tf = float(dedup_dim) * dedup_rows * (dedup_rows - 1) / (dedup_ms / 1e3) / 1e12
-            line["dedup"] = {"workload": f"all pairs cos >= 0.95 over {dedup_rows} x {dedup_dim} bf16 rows (tcgen05; "
-                                         "useful-triangle flops; the 8-GPU 2M-row run is tools/bench_dedup_sharded.py)",
-                             "ms": dedup_ms, "tflops": tf, "frac_of_bf16_burst": tf / peaks["bf16_tflops"],
-                             "frac_of_bf16_sustained": tf / peaks["bf16_tflops_sustained"]}
+        if f32_info:
+            line["f32_1m"] = f32_info
+        if dedup_info:
+            nd = dedup_info["rows"]
+            tf = float(dedup_dim) * nd * (nd - 1) / (dedup_ms / 1e3) / 1e12
+            line["dedup"] = {"workload": f"all pairs cos >= 0.95 over {nd} x {dedup_dim} bf16 rows, 1 % planted near-duplicates "
+                                         f"(tcgen05; useful-triangle flops; "
+                                         f"{'triangle split over %d ranks after an NCCL replicate' % G if G > 1 else 'one GPU'})",
+                             "ms": dedup_ms, "tflops": tf, "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
+                             "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"],
+                             "pairs_found": dedup_info["pairs_found"], "pairs_planted": dedup_info["pairs_planted"],
+                             "count_ok": dedup_info["count_ok"], "replicate_s": dedup_info["replicate_s"]}
         if G == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_qps(args.rows, args.dim, k, budget_s=args.cpu_budget)
         print(json.dumps(line))
-    ix.close()
+    if not ix_closed:
+        ix.close()
     if G > 1:
         dist.destroy_process_group()
+
+
+def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, tol):
+    """rank 0 only: build the corpus again as ONE single-process collection over all G GPUs and answer one
+    request at a time through vs_group_query_host (what a uvicorn worker would call)."""
+    n = args.rows
+    chunk = 1 << 19
+    t0 = time.perf_counter()
+    gx = M.GroupIndex(args.dim, args.dtype, devices=list(range(G)), capacity=n, b_max=64, k_max=max(32, args.k))
+    for s, sh in enumerate(gx.shards):
+        dv = torch.device("cuda", sh.device)
+        g = torch.Generator(device=dv)
+        n_s = (n - s + G - 1) // G
+        with torch.cuda.device(dv):
+            for c0 in range(0, n_s, chunk):
+                sh.add(corpus_chunk(c0 + s * 7919, min(chunk, n_s - c0), args.dim, seed=4321, device=dv, g=g))
+            torch.cuda.synchronize()
+    assert len(gx) == n
+    for order in plants:
+        for g_row, v in order:
+            gx.shards[g_row % G].set_row(g_row // G, v)
+    build_s = time.perf_counter() - t0
+    k = args.k
+    # parity of this path too
+    s, r = gx.query(pq, k, mode="scan")
+    ok, why = check_planted(r, s, plants, want_scores, tol)
+    s1 = np.concatenate([gx.query(pq[j:j + 1], k, mode="scan")[1] for j in range(len(pq))])
+    ok = ok and np.array_equal(s1, r)
+    rng = np.random.default_rng(7)
+    qs = rng.standard_normal((256, args.dim)).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    for i in range(16):
+        gx.query(qs[i:i + 1], k, mode="scan")
+    nq = args.group_queries
+    lat = np.empty(nq)
+    w0 = time.perf_counter()
+    for i in range(nq):
+        a = time.perf_counter()
+        gx.query(qs[i % 256:i % 256 + 1], k, mode="scan")
+        lat[i] = time.perf_counter() - a
+    wall = time.perf_counter() - w0
+    out = {"value": nq / wall, "unit": "queries/s", "n_gpus": G, "queries": nq,
+           "latency_us": {"p50": float(np.percentile(lat, 50) * 1e6), "p99": float(np.percentile(lat, 99) * 1e6),
+                          "min": float(lat.min() * 1e6)},
+           "path": f"GroupIndex.query -> vs_group_query_host: ONE process, {G} GPU(s), one request at a time; query through a pinned "
+                   "host-mapped area, one fused scan launch per GPU (exchange over NVLink inside the kernel), result + flag "
+                   "written to host-mapped memory by the kernel, polled by the caller (no stream synchronise)",
+           "h2d_bytes_per_query": args.dim * 4 * G, "d2h_bytes_per_query": k * 12,
+           "planted_ok": bool(ok), "first_problem": why or None, "build_s": build_s}
+    if args.dtype == "bf16" and args.batch > 0:
+        B = args.batch
+        img = rng.standard_normal((B, args.dim)).astype(np.float32)
+        txt = rng.standard_normal((B, args.dim)).astype(np.float32)
+        w = rng.random(B)
+        gx.query_multimodal(img, txt, w, k, mode="tensor")
+        b0 = time.perf_counter()
+        for _ in range(3):
+            gx.query_multimodal(img, txt, w, k, mode="tensor")
+        bms = (time.perf_counter() - b0) / 3 * 1e3
+        out["batched_multimodal_host"] = {"workload": f"{B} (image, text, weight) triples from host memory -> blend + K2 on every GPU + "
+                                                      "exchange -> [B, k] on the host (BASELINE config 3, end to end)",
+                                          "ms_per_batch": bms, "qps": B / (bms / 1e3)}
+    gx.close()
+    return out
 
 
 def main():
@@ -525,20 +792,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--blocks", type=int, default=3, help="timed blocks of exactly --steps steps; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=TOTAL_ROWS)
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--k", type=int, default=TOPK)
-    ap.add_argument("--queries", type=int, default=32, help="single-query scans per step")
+    ap.add_argument("--queries", type=int, default=32, help="single-query scans per step PER GPU (a step = queries x N scans)")
     ap.add_argument("--batch", type=int, default=1024, help="batched tensor-path extra (0 = skip)")
     ap.add_argument("--filters", type=int, default=256, help="filter-sweep extra: number of prompts (0 = skip)")
-    ap.add_argument("--dedup-rows", type=int, default=200_000, help="dedup extra (N=1 only): rows x 768 (0 = skip)")
+    ap.add_argument("--f32-rows", type=int, default=1_000_000, help="config-2 extra (N=1 only): rows of the f32 corpus (0 = skip)")
+    ap.add_argument("--dedup-rows", type=int, default=2_000_000, help="config-5 extra: rows x 768 (0 = skip)")
+    ap.add_argument("--group-queries", type=int, default=400,
+                    help="one-request-at-a-time queries through the single-process group (0 = skip)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: candidate exchange fused into the query kernel over NVLink peer memory, or NCCL all-gather")
     ap.add_argument("--hnsw-rows", type=int, default=20_000,
                     help="reference arm: rows of the bounded HNSW recall sample (0 = skip)")
-    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--cpu-budget", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

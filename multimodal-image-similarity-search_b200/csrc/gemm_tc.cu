@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -44,6 +45,8 @@ constexpr int kTcMaxStages = 8;
 constexpr int kInvRing = 4;          // tiles of inverse norms staged ahead of the epilogue
 constexpr int kTcBarrierBytes = 512; // mbarriers + TMEM address holder
 constexpr int kTcSmemMax = 232448; // 227 KB
+constexpr int kTcMaxBatch = 4096;  // queries / prompts per launch (the partial-list workspace is sized for it)
+constexpr int kFilterClusterCap = 8;
 
 enum { kModeTopK = 0, kModeFilter = 1, kModeDedup = 2 };
 
@@ -63,14 +66,16 @@ struct TcParams {
   int n_items;             // work items per cluster sequence
   int a_stream;            // 1: the A block is NOT resident; its k-block travels with every B stage (wide rows)
   int prefetch;            // B stages to prefetch into L2 ahead of the smem ring
-  int debug_noepi;         // VS_TC_DEBUG_NOEPI=1: epilogue only hands the accumulator back (profiling aid)
-  unsigned long long* dbg; // VS_TC_DEBUG_COUNT=1: [groups, slow-path entries, lanes that hit, inserts]
+  int n_agroups;           // A-block groups of C blocks each: work item w = (slice w / n_agroups, A group w % n_agroups)
   const float* gmin;       // [ceil(n_rows/32)] (1 - 2^-20) * min row norm of each 32-row group (+inf if empty)
   // top-k
   uint32_t* gbound;        // [Bp][pool stride] orderable keys: per query k class maxima (row % k) over everything ANY
                            // slice / epilogue half has inserted; their minimum is a lower bound on the k-th score
-  int k_real;              // slots of the pool in use (= k)
-  int pool_mode;           // 1: shared pool (default); 0: one key per query = max of the lists' own k-th scores
+  int k_real;              // slots of the pool in use (= k of this round)
+  // rounds for 32 < k <= 128 (see launch_tensor_topk): only rows ranking strictly AFTER (ub_s[q], ub_r[q]) compete
+  const float* ub_s;       // [B] stride ub_stride, or nullptr (first round)
+  const int64_t* ub_r;
+  int ub_stride;
   float* part_s;           // [n_slices][2][Bp][KL]  (2 = the two epilogue halves)
   int64_t* part_r;
   int Bp;                  // C * 128
@@ -409,8 +414,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       t0 = a_row0 / BN;       // only columns j > i can pair with row i
       t1 = p.n_tiles;
     } else {
-      ablock = (int)rank;
-      t0 = (uint32_t)w * p.tiles_per_slice;
+      // the clusters (slice, 0 .. n_agroups-1) stream the same tiles at the same time: the slice comes from HBM
+      // once and from L2 for the other A groups
+      ablock = (w % p.n_agroups) * C + (int)rank;
+      t0 = (uint32_t)(w / p.n_agroups) * p.tiles_per_slice;
       t1 = min(t0 + (uint32_t)p.tiles_per_slice, p.n_tiles);
     }
   };
@@ -565,28 +572,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // halves) that work on the same query through gbound[] (atomicMax on orderable keys).  A row
       // scoring strictly below it cannot be in the global top-k.
       uint32_t* gb_ptr = nullptr;
-      float published = VS_NEG_INF;
       constexpr int KLP = pool_stride(KL);
-      if (MODE == kModeTopK) gb_ptr = p.gbound + ((size_t)ablock * kTcM + m_local) * KLP;
+      bool has_ub = false;
+      float ub_s = 0.f;
+      int64_t ub_r = 0;
+      if (MODE == kModeTopK) {
+        gb_ptr = p.gbound + ((size_t)ablock * kTcM + m_local) * KLP;
+        if (p.ub_s != nullptr && ablock * kTcM + m_local < p.F) {
+          has_ub = true;
+          ub_s = __ldg(p.ub_s + (size_t)(ablock * kTcM + m_local) * p.ub_stride);
+          ub_r = __ldg(p.ub_r + (size_t)(ablock * kTcM + m_local) * p.ub_stride);
+          if (ub_r < 0) ub_s = VS_NEG_INF;   // the previous round ran out of rows: nothing is left for this query
+        }
+      }
       for (uint32_t t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t acc = tile_ctr % ACC;
         float gb = VS_NEG_INF;
-        if (MODE == kModeTopK && p.debug_noepi != 4) {
+        if (MODE == kModeTopK) {
           int unused;
-          gb = key_score(p.pool_mode ? pool_min<KLP>(gb_ptr, p.k_real, unused) : *reinterpret_cast<volatile uint32_t*>(gb_ptr));
+          gb = key_score(pool_min<KLP>(gb_ptr, p.k_real, unused));
         }
         mbar_wait(&tfull[acc], (tile_ctr / ACC) & 1);
         tc_fence_after();
         const uint32_t ib = tile_ctr % kInvRing;
         mbar_wait(&ifull[ib], (tile_ctr / kInvRing) & 1);
         const uint32_t row0 = t * BN;
-        const int n_groups = p.debug_noepi == 1 ? 0 : BN / 32;   // debug_noepi: profiling aid (see TcParams)
+#ifdef VS_TC_NOEPI   // profiling build: the epilogue only hands the accumulator back (mainloop ceiling)
+        constexpr int n_groups = 0;
+#else
+        constexpr int n_groups = BN / 32;
+#endif
 #pragma unroll 1
         for (int g = half; g < n_groups; g += 2) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
           const uint32_t rg = row0 + g * 32;
-          if (MODE == kModeTopK && p.pool_mode && t - t0 < 2u && p.debug_noepi != 4) {
+          if (MODE == kModeTopK && t - t0 < 2u) {
             // warm-up: the pool fills within the first groups of an item; pick the bound up per group
             int unused;
             gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
@@ -627,13 +648,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             } else {
               hit = p.tau > 0.f ? (m * inv_a >= p.tau * gmn) : (nvalid > 0);
             }
-            if (p.debug_noepi == 2) hit = false;
-            if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1ull);
-            if (p.debug_noepi != 3 && __any_sync(0xffffffffu, hit)) {
-              if (p.dbg) {
-                if (lane == 0) atomicAdd(p.dbg + 1, 1ull);
-                if (hit) atomicAdd(p.dbg + 2, 1ull);
-              }
+            if (__any_sync(0xffffffffu, hit)) {
               // ---- slow path (compact on purpose: one insert site, no per-column code copies) ----
               // exact scores + a per-lane bitmask of candidate columns, then candidates are pulled
               // out in ascending column (= row) order with a select tree (no dynamic register index)
@@ -648,6 +663,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
               }
               const float thr0 = top.threshold();
+              [[maybe_unused]] const int64_t grow0 = (int64_t)rg * p.row_stride + p.row_base;   // reported row of column 0
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 bool c;
@@ -678,10 +694,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   const uint32_t row = rg + j;
                   if (MODE == kModeTopK) {
                     if (s > top.threshold()) {
-                      if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
                       if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) {
                         top.insert(s, row);
-                        if (p.pool_mode && p.debug_noepi != 4) atomicMax(gb_ptr + row % (uint32_t)p.k_real, score_key(s));
+                        atomicMax(gb_ptr + row % (uint32_t)p.k_real, score_key(s));
                       }
                     }
                   } else {
@@ -705,14 +720,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           else mbar_arrive(&tempty[acc]);
           mbar_arrive(&iempty[ib]);
         }
-        if (MODE == kModeTopK && !p.pool_mode && p.debug_noepi != 4 && top.threshold() > published) {
-          published = top.threshold();
-          atomicMax(gb_ptr, score_key(published));
-        }
       }
       if (MODE == kModeTopK) {
         // partial lists: [slice][half][Bp][KL]
-        const size_t base = (((size_t)w * 2 + half) * p.Bp + (size_t)ablock * kTcM + m_local) * KL;
+        const size_t base = (((size_t)(w / p.n_agroups) * 2 + half) * p.Bp + (size_t)ablock * kTcM + m_local) * KL;
 #pragma unroll
         for (int j = 0; j < KL; ++j) {
           p.part_s[base + j] = top.s[j];
@@ -741,6 +752,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= Bp) return;
   if (gbound && lane < pool_stride_words) gbound[(size_t)b * pool_stride_words + lane] = score_key(VS_NEG_INF);
+  if (q == nullptr) return;   // a later round of 32 < k <= 128: the queries are already in place, only the pool is reset
   __nv_bfloat16* o = out + (size_t)b * Dp;
   if (b >= B) {
     for (int e = lane; e < Dp; e += 32) o[e] = __float2bfloat16_rn(0.f);
@@ -789,21 +801,26 @@ static cudaError_t make_map(CUtensorMap* map, const void* base, uint64_t rows, u
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Tuning knobs.  The PRODUCT library has none: every value below is a constant.  A tuning build
+// (`VS_BUILD_TUNING=1 python build.py` -> -DVS_TUNING, a separate .so loaded through VS_LIB_PATH by
+// tools/bench_tensor.py) reads VS_TC_* from the environment for A/B runs on the box.
 static int env_int(const char* name, int dflt) {
+#ifdef VS_TUNING
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
 }
 static int tc_block_n() {
   static int bn = env_int("VS_TC_BN", 256) == 128 ? 128 : 256;
   return bn;
 }
-// largest cluster size allowed (1, 2, 4 or 8); tuned on B200, see profiles/
-static int tc_max_cluster() {
-  static int c = [] {
-    const int v = env_int("VS_TC_CLUSTER", 8);
-    return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
-  }();
-  return c;
+// largest cluster size allowed (1, 2, 4 or 8)
+static int tc_max_cluster(int dflt) {
+  const int v = env_int("VS_TC_CLUSTER", dflt);
+  return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
 }
 
 struct TcPlan {
@@ -811,10 +828,8 @@ struct TcPlan {
   size_t smem;
   bool ok;
 };
-// cg_request: 0 = auto, 1 / 2 = force the issue mode; +16 = prefer a resident A block in pair mode
-static bool resident_request(int env_flag, int cg_request) { return env_flag != 0 || (cg_request & 16) != 0; }
-static TcPlan plan_for_cg(int dim, int cg_request_in) {
-  const int cg_request = cg_request_in & 15;
+// cg_request: 0 = auto, 1 / 2 = force the issue mode
+static TcPlan plan_for_cg(int dim, int cg_request) {
   TcPlan pl;
   pl.kb_count = (dim + kTcKB - 1) / kTcKB;
   pl.Dp = pl.kb_count * kTcKB;
@@ -826,23 +841,18 @@ static TcPlan plan_for_cg(int dim, int cg_request_in) {
   // Resident A needs kb_count x 16 KB of smem.  At dim 768 that left 2 x 16 KB of B stages and the
   // kernel was TMA-latency bound (dedup 200k x 768: 0.45 PFLOP/s).  Streaming the A k-block with every
   // stage instead (16 KB more L2->SM traffic per stage, A block stays L2 resident) gives a 4-deep
-  // ring of BN = 256 tiles at ANY dim: dedup 1.10 PFLOP/s, and the 512-d top-k gains 8 % as well
-  // (profiles/r01_tensor_path.md), so it is the default; VS_TC_ASTREAM=0 keeps A resident.
+  // ring of BN = 256 tiles at ANY dim (profiles/r01_tensor_path.md); VS_TC_ASTREAM=0 keeps A resident.
   static const int force_stream = env_int("VS_TC_ASTREAM", -1);
   const bool resident_ok = a_bytes + fixed + 2 * 128 * 128 <= (size_t)kTcSmemMax;
   pl.a_stream = force_stream >= 0 ? (force_stream != 0 || !resident_ok || stages_for(pl.BN) < 2) : 1;
-  // CTA pairs (tcgen05 cta_group::2): needs streamed A, BN = 256 and an even cluster; VS_TC_CG=1 = single-CTA
-  // MMAs.  The pair mainloop is 4 % faster (1.30 vs 1.25 PFLOP/s with the epilogue compiled out) but the
-  // leader's next MMA into an accumulator buffer waits for the epilogues of BOTH CTAs, so it only pays
-  // once the top-k slow path is rare (shared pool bound): 1.147 vs 1.138 (K2), 1.02 vs 1.01 (K3).
+  // CTA pairs (tcgen05 cta_group::2): needs BN = 256 and an even cluster; VS_TC_CG=1 = single-CTA MMAs.
   static const int want_cg = env_int("VS_TC_CG", 2);
   if (pl.a_stream && pl.BN == 256 && want_cg == 2 && cg_request != 1) pl.cg = 2;
-  // Pair mode with a RESIDENT A block (default when >= 4 stages of 16 KB fit beside it, i.e. dim <= 512;
-  // VS_TC_ARES2=0 streams A always): each CTA then receives only its half B tile per stage (16 KB
-  // instead of 16 + 16 KB).  Measured at dim 512: K2 1.148 -> 1.172, K3 1.059 -> 1.114 (few A blocks ->
-  // clusters of 2, no wider multicast: it was at the 64 B/clk L2->SM limit), K4 1.11 -> 1.19 PFLOP/s.
+  // Pair mode with a RESIDENT A block (when >= 4 stages of 16 KB fit beside it, i.e. dim <= 512): each CTA
+  // then receives only its half B tile per stage (16 KB instead of 16 + 16 KB).  Measured at dim 512:
+  // K2 1.148 -> 1.172, K3 1.059 -> 1.114, K4 1.11 -> 1.19 PFLOP/s.
   static const int ares2 = env_int("VS_TC_ARES2", 1);
-  if (pl.cg == 2 && resident_request(ares2, cg_request_in)) {
+  if (pl.cg == 2 && ares2 != 0) {
     const size_t stride = (size_t)pl.BN * 128 / 2;
     const int st2 = a_bytes + fixed <= (size_t)kTcSmemMax ? (int)(((size_t)kTcSmemMax - fixed - a_bytes) / stride) : 0;
     if (st2 >= 4) {
@@ -873,13 +883,14 @@ static TcPlan plan_for_cg(int dim, int cg_request_in) {
 static TcPlan plan_for(int dim) { return plan_for_cg(dim, 0); }
 
 static int kl_for(int k) { return k <= 10 ? 10 : 32; }
-static int cluster_for(int chunks) {
+// cluster size for `chunks` A blocks: the largest power of two <= min(chunks, cap)
+static int cluster_for(int chunks, int cap) {
   int c = 1;
-  while (c * 2 <= chunks && c * 2 <= tc_max_cluster()) c *= 2;
+  while (c * 2 <= chunks && c * 2 <= cap) c *= 2;
   return c;
 }
 
-// workspace layout: [gbound u32 x Bp][queries bf16 Bp x Dp][partial lists]
+// workspace layout: [gbound u32 x Bp x 32][queries bf16 Bp x Dp][partial lists]
 struct TcWorkspace {
   uint32_t* gbound;
   __nv_bfloat16* q;
@@ -899,48 +910,34 @@ static TcWorkspace carve_workspace(void* base, int B, int dim, int k, int sm_cou
   w.q = reinterpret_cast<__nv_bfloat16*>(p + off);
   off += up((size_t)Bp * pl.Dp * 2);
   w.parts = reinterpret_cast<float*>(p + off);
-  off += (size_t)2 * sm_count * 8 * kTcM * KL * 12 + 1024;   // <= sm_count slices x 2 halves x (8 x 128) queries
+  // partial lists [n_slices][2 halves][Bp][KL] (f32 score + i64 row); n_slices <= sm_count
+  off += up((size_t)2 * sm_count * Bp * KL * 4) + up((size_t)2 * sm_count * Bp * KL * 8) + 1024;
   w.total = off;
   return w;
 }
 size_t tensor_workspace_bytes(int B, int dim, int k, int sm_count) {
-  return carve_workspace(nullptr, B, dim, k, sm_count).total;
+  // one launch covers at most kTcMaxBatch queries (launch_tensor_topk loops beyond that)
+  return carve_workspace(nullptr, B < kTcMaxBatch ? B : kTcMaxBatch, dim, k, sm_count).total;
 }
 static int tc_prefetch() {
   static int v = env_int("VS_TC_PREFETCH", 0);   // measured on B200: no gain for top-k, a loss for the sweep
   return v < 0 ? 0 : v > 64 ? 64 : v;
 }
 
+// Per (kernel instantiation, smem size): the dynamic-smem attribute is set once and the number of co-resident
+// clusters is asked once -- neither belongs on the per-query path.
 template <int MODE, int BN, int KL, int C, int CG>
-static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const TcPlan& pl,
-                               int n_clusters_wanted, cudaStream_t st) {
+static int prepared_clusters(const TcPlan& pl, int sm_count) {
+  static std::mutex mu;
+  static size_t cached_smem = 0;
+  static int cached_n = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cached_smem == pl.smem && cached_n > 0) return cached_n;
   auto kern = tc_kernel<MODE, BN, KL, C, CG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_clusters_wanted * C), 1, 1);
-  cfg.blockDim = dim3(kTcThreads, 1, 1);
-  cfg.dynamicSmemBytes = pl.smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
-  count_launch();
-  return e;
-}
-
-// how many clusters of size C (with this kernel's smem) can be co-resident
-template <int MODE, int BN, int KL, int C, int CG>
-static int max_clusters(const TcPlan& pl, int sm_count) {
-  auto kern = tc_kernel<MODE, BN, KL, C, CG>;
+  int n = sm_count / C;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
     cudaGetLastError();
-    return sm_count / C;
+    return -1;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(sm_count / C * C), 1, 1);
@@ -953,12 +950,33 @@ static int max_clusters(const TcPlan& pl, int sm_count) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
-    cudaGetLastError();
-    n = sm_count / C;
-  }
+  int q = 0;
+  if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0) n = q;
+  else cudaGetLastError();
+  cached_smem = pl.smem;
+  cached_n = n;
   return n;
+}
+
+template <int MODE, int BN, int KL, int C, int CG>
+static cudaError_t launch_tc_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, const TcPlan& pl,
+                               int n_clusters_wanted, cudaStream_t st) {
+  auto kern = tc_kernel<MODE, BN, KL, C, CG>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_clusters_wanted * C), 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  count_launch();
+  return e;
 }
 
 // CG = 2 (CTA pairs) exists for BN = 256 and even clusters only; `pl.cg` selects it at run time
@@ -1000,80 +1018,81 @@ static void fill_common(TcParams& p, const TensorArgs& a, const TcPlan& pl) {
   p.stages = pl.stages;
   p.a_stream = pl.a_stream;
   p.prefetch = tc_prefetch();
-  static const int noepi = env_int("VS_TC_DEBUG_NOEPI", 0);
-  p.debug_noepi = noepi;
+  p.n_agroups = 1;
 }
 
-static void plan_slices(TcParams& p, int n_clusters) {
-  p.n_slices = n_clusters < (int)p.n_tiles ? n_clusters : (int)p.n_tiles;
-  if (p.n_slices < 1) p.n_slices = 1;
-  p.tiles_per_slice = (int)((p.n_tiles + p.n_slices - 1) / p.n_slices);
+// n_clusters resident clusters, n_agroups A groups: (slices x A groups) work items, the A groups of one slice on
+// neighbouring clusters so that they stream the same tiles together
+static void plan_slices(TcParams& p, int n_clusters, int n_agroups) {
+  p.n_agroups = n_agroups;
+  int slices = n_clusters / n_agroups;
+  if (slices < 1) slices = 1;
+  if (slices > (int)p.n_tiles) slices = (int)p.n_tiles;
+  p.tiles_per_slice = (int)((p.n_tiles + slices - 1) / slices);
   p.n_slices = (int)((p.n_tiles + p.tiles_per_slice - 1) / p.tiles_per_slice);
-  p.n_items = p.n_slices;
+  p.n_items = p.n_slices * n_agroups;
 }
 
 static bool dims_ok(const TensorArgs& a) { return tensor_dim_ok(a.dim) && a.ld_elems % 8 == 0; }
 bool tensor_dim_ok(int dim) { return dim >= 8 && dim % 8 == 0 && dim <= 4096; }
 
+// ub extraction for the rounds of 32 < k <= 128: nothing to launch -- round r reads the (score, row) at
+// out[b][32 r - 1] of the result buffer itself (written by round r-1's merge, stream ordered).
 cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k, void* workspace, float* out_s,
                                int64_t* out_r, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
-  if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || B <= 0) return cudaErrorNotSupported;
-  const int Bp = (B + kTcM - 1) / kTcM * kTcM;
-  const int KL = kl_for(k);
-  const TcWorkspace ws = carve_workspace(workspace, B, a.dim, k, sm_count);
-  __nv_bfloat16* qb = ws.q;
-  float* part_s = ws.parts;
-
-  const int KLP = pool_stride(KL);
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(q, B, a.dim, Bp, pl.Dp, qb, ws.gbound, KLP);
-  count_launch();
-  if (!a.gmin) return cudaErrorInvalidValue;
-
-  const int chunks_total = Bp / kTcM;
-  for (int c0 = 0; c0 < chunks_total;) {
-    const int C = cluster_for(chunks_total - c0);
+  if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || k <= 0 || B <= 0 || !a.gmin) return cudaErrorNotSupported;
+  // K2 default: clusters of 8 when there are >= 8 query blocks (one corpus stream shared by 1024 queries)
+  static const int cap = tc_max_cluster(8);
+  for (int b0 = 0; b0 < B; b0 += kTcMaxBatch) {
+    const int nb = B - b0 < kTcMaxBatch ? B - b0 : kTcMaxBatch;
+    const int Bp = (nb + kTcM - 1) / kTcM * kTcM;
+    const int chunks = Bp / kTcM;
+    const int C = cluster_for(chunks, cap);
+    const int n_agroups = (chunks + C - 1) / C;
+    const int Bpp = n_agroups * C * kTcM;             // padded to whole A groups
     const int cg = C >= 2 ? pl.cg : 1;
     const TcPlan plc = plan_for_cg(a.dim, cg);
-    TcParams p;
-    fill_common(p, a, plc);
-    p.gmin = a.gmin;
-    p.gbound = ws.gbound + (size_t)c0 * kTcM * KLP;
-    p.k_real = k;
-    static const int pool_mode = env_int("VS_TC_POOL", 1);
-    p.pool_mode = pool_mode;
-    const int ncl = VS_TC_DISPATCH(max_clusters, kModeTopK, plc.BN, KL, C, cg, plc, sm_count);
-    plan_slices(p, ncl);
-    p.Bp = C * kTcM;
-    p.part_s = part_s;
-    p.part_r = reinterpret_cast<int64_t*>(((uintptr_t)(part_s + (size_t)2 * p.n_slices * p.Bp * KL) + 255) & ~(uintptr_t)255);
+    const int k_list = k <= 32 ? k : 32;              // per round
+    const int KL = kl_for(k_list);
+    const int KLP = pool_stride(KL);
+    const TcWorkspace ws = carve_workspace(workspace, Bpp, a.dim, k_list, sm_count);
+    const int ncl = VS_TC_DISPATCH(prepared_clusters, kModeTopK, plc.BN, KL, C, cg, plc, sm_count);
+    if (ncl <= 0) return cudaErrorLaunchOutOfResources;
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
+    cudaError_t e = make_map(&tmA, ws.q, (uint64_t)Bpp, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
     e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
     if (e != cudaSuccess) return e;
-    static const int dbg_count = env_int("VS_TC_DEBUG_COUNT", 0);
-    unsigned long long* dbg = nullptr;
-    if (dbg_count) {
-      cudaMalloc(&dbg, 4 * sizeof(unsigned long long));
-      cudaMemsetAsync(dbg, 0, 4 * sizeof(unsigned long long), st);
-      p.dbg = dbg;
+    float* o_s = out_s + (size_t)b0 * k;
+    int64_t* o_r = out_r + (size_t)b0 * k;
+    for (int k0 = 0; k0 < k; k0 += 32) {              // rounds: ranks [k0, k0 + 32) of every query
+      const int kr = k - k0 < 32 ? k - k0 : 32;
+      // (re)normalise + round the queries only once; the pool of class maxima is reset every round
+      prep_queries_kernel<<<(Bpp + 7) / 8, 256, 0, st>>>(k0 == 0 ? q + (size_t)b0 * a.dim : nullptr, nb, a.dim, Bpp, pl.Dp,
+                                                         ws.q, ws.gbound, KLP);
+      count_launch();
+      TcParams p;
+      fill_common(p, a, plc);
+      p.gmin = a.gmin;
+      p.gbound = ws.gbound;
+      p.k_real = kr;
+      p.F = nb;
+      if (k0 > 0) {
+        p.ub_s = o_s + (k0 - 1);
+        p.ub_r = o_r + (k0 - 1);
+        p.ub_stride = k;
+      }
+      plan_slices(p, ncl, n_agroups);
+      p.Bp = Bpp;
+      p.part_s = ws.parts;
+      p.part_r = reinterpret_cast<int64_t*>(((uintptr_t)(ws.parts + (size_t)2 * p.n_slices * p.Bp * KL) + 255) & ~(uintptr_t)255);
+      const int grid_clusters = p.n_items < ncl ? p.n_items : ncl;
+      e = VS_TC_DISPATCH(launch_tc_c, kModeTopK, plc.BN, KL, C, cg, tmA, tmB, p, plc, grid_clusters, st);
+      if (e != cudaSuccess) return e;
+      e = launch_merge_ex(p.part_s, p.part_r, 2 * p.n_slices, p.Bp, nb, KL, kr, o_s + k0, o_r + k0, st, k);
+      if (e != cudaSuccess) return e;
     }
-    e = VS_TC_DISPATCH(launch_tc_c, kModeTopK, plc.BN, KL, C, cg, tmA, tmB, p, plc, p.n_slices, st);
-    if (e != cudaSuccess) return e;
-    if (dbg) {
-      unsigned long long h[4];
-      cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
-      fprintf(stderr, "[tc dbg] C=%d slices=%d tiles/slice=%d: warp-groups=%llu slow-entries=%llu (%.1f%%) hit-lanes=%llu inserts=%llu\n",
-              C, p.n_slices, p.tiles_per_slice, h[0], h[1], 100.0 * h[1] / (h[0] ? h[0] : 1), h[2], h[3]);
-      cudaFree(dbg);
-    }
-    const int nb = (B - c0 * kTcM) < C * kTcM ? (B - c0 * kTcM) : C * kTcM;
-    e = launch_merge_ex(p.part_s, p.part_r, 2 * p.n_slices, p.Bp, nb, KL, k, out_s + (size_t)c0 * kTcM * k,
-                        out_r + (size_t)c0 * kTcM * k, st);
-    if (e != cudaSuccess) return e;
-    c0 += C;
   }
   return cudaSuccess;
 }
@@ -1082,32 +1101,37 @@ cudaError_t launch_tensor_filter(const TensorArgs& a, const float* prompts, int 
                                  uint32_t* out_bits, int64_t words_per_filter, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a) || F <= 0) return cudaErrorNotSupported;
-  const int Bp = (F + kTcM - 1) / kTcM * kTcM;
-  const TcWorkspace ws = carve_workspace(workspace, F, a.dim, 1, sm_count);
-  __nv_bfloat16* qb = ws.q;
-  prep_queries_kernel<<<(Bp + 7) / 8, 256, 0, st>>>(prompts, F, a.dim, Bp, pl.Dp, qb, nullptr, 0);
-  count_launch();
-  const int chunks_total = Bp / kTcM;
-  for (int c0 = 0; c0 < chunks_total;) {
-    const int C = cluster_for(chunks_total - c0);
+  // K3 default cluster cap (tuned on B200, profiles/r02_tensor_path.md)
+  static const int cap = tc_max_cluster(kFilterClusterCap);
+  for (int f0 = 0; f0 < F; f0 += kTcMaxBatch) {
+    const int nf = F - f0 < kTcMaxBatch ? F - f0 : kTcMaxBatch;
+    const int Bp = (nf + kTcM - 1) / kTcM * kTcM;
+    const int chunks = Bp / kTcM;
+    const int C = cluster_for(chunks, cap);
+    const int n_agroups = (chunks + C - 1) / C;
+    const int Bpp = n_agroups * C * kTcM;
     const int cg = C >= 2 ? pl.cg : 1;
     const TcPlan plc = plan_for_cg(a.dim, cg);
+    const TcWorkspace ws = carve_workspace(workspace, Bpp, a.dim, 1, sm_count);
+    prep_queries_kernel<<<(Bpp + 7) / 8, 256, 0, st>>>(prompts + (size_t)f0 * a.dim, nf, a.dim, Bpp, pl.Dp, ws.q, nullptr, 0);
+    count_launch();
     TcParams p;
     fill_common(p, a, plc);
-    const int ncl = VS_TC_DISPATCH10(max_clusters, kModeFilter, plc.BN, C, cg, plc, sm_count);
-    plan_slices(p, ncl);
-    p.out_bits = out_bits + (size_t)c0 * kTcM * words_per_filter;
+    const int ncl = VS_TC_DISPATCH10(prepared_clusters, kModeFilter, plc.BN, C, cg, plc, sm_count);
+    if (ncl <= 0) return cudaErrorLaunchOutOfResources;
+    plan_slices(p, ncl, n_agroups);
+    p.out_bits = out_bits + (size_t)f0 * words_per_filter;
     p.words_per_filter = words_per_filter;
     p.tau = tau;
-    p.F = F - c0 * kTcM;
+    p.F = nf;
     CUtensorMap tmA, tmB;
-    cudaError_t e = make_map(&tmA, qb + (size_t)c0 * kTcM * pl.Dp, (uint64_t)C * kTcM, pl.Dp, pl.Dp, kTcM);
+    cudaError_t e = make_map(&tmA, ws.q, (uint64_t)Bpp, pl.Dp, pl.Dp, kTcM);
     if (e != cudaSuccess) return e;
     e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
     if (e != cudaSuccess) return e;
-    e = VS_TC_DISPATCH10(launch_tc_c, kModeFilter, plc.BN, C, cg, tmA, tmB, p, plc, p.n_slices, st);
+    const int grid_clusters = p.n_items < ncl ? p.n_items : ncl;
+    e = VS_TC_DISPATCH10(launch_tc_c, kModeFilter, plc.BN, C, cg, tmA, tmB, p, plc, grid_clusters, st);
     if (e != cudaSuccess) return e;
-    c0 += C;
   }
   return cudaSuccess;
 }
@@ -1116,13 +1140,13 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
                                 int64_t* out_i, int64_t* out_j, float* out_score, unsigned long long* out_count,
                                 void* workspace, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
-  if (!pl.ok || !dims_ok(a)) return cudaErrorNotSupported;
+  if (!pl.ok || !dims_ok(a) || !a.gmin) return cudaErrorNotSupported;
   (void)workspace;
-  if (!a.gmin) return cudaErrorInvalidValue;
+  static const int ccap = tc_max_cluster(8);
   const int64_t a_row_min = row_lo;
   row_lo = row_lo / kTcM * kTcM;   // A blocks are 128-row aligned; rows below the caller's row_lo are filtered out
   const int n_blocks = (int)((row_hi - row_lo + kTcM - 1) / kTcM);
-  const int C = cluster_for(n_blocks);
+  const int C = cluster_for(n_blocks, ccap);
   const int cg = C >= 2 ? pl.cg : 1;
   const TcPlan plc = plan_for_cg(a.dim, cg);
   TcParams p;
@@ -1143,7 +1167,8 @@ cudaError_t launch_tensor_dedup(const TensorArgs& a, int64_t row_lo, int64_t row
   if (e != cudaSuccess) return e;
   e = make_map(&tmB, a.rows, a.n_rows, a.dim, a.ld_elems, plc.BN / C);
   if (e != cudaSuccess) return e;
-  int ncl = VS_TC_DISPATCH10(max_clusters, kModeDedup, plc.BN, C, cg, plc, sm_count);
+  int ncl = VS_TC_DISPATCH10(prepared_clusters, kModeDedup, plc.BN, C, cg, plc, sm_count);
+  if (ncl <= 0) return cudaErrorLaunchOutOfResources;
   if (ncl > p.n_items) ncl = p.n_items;
   return VS_TC_DISPATCH10(launch_tc_c, kModeDedup, plc.BN, C, cg, tmA, tmB, p, plc, ncl, st);
 }

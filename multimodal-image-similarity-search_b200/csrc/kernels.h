@@ -9,7 +9,7 @@ namespace vs {
 
 constexpr int kMaskWords = 4;
 constexpr int kMaxFusedK = 128;   // register-list top-k limit of the fused scan kernel
-constexpr int kMaxTensorK = 32;   // per-thread register list limit of the tcgen05 top-k epilogue
+constexpr int kMaxTensorK = 128;  // tcgen05 top-k: per-thread register lists of 32, ceil(k / 32) exact rounds
 constexpr int kMaxK = 1024;
 constexpr int kScanMaxCtasPerSm = 4;   // the partial-list workspace is sized for this many CTAs per SM
 
@@ -81,9 +81,9 @@ cudaError_t preload_exchange_kernels();
 // what: 3 = push + wait + merge (one exchange), 1 = push only, 2 = wait + merge only (deferred collect)
 cudaError_t launch_exchange_merge(const float* cs, const int64_t* cr, const XchgParams& x, int B, int k, float* out_s,
                                   int64_t* out_r, int sm_count, cudaStream_t st, int what = 3);
-// general form: candidates [G][Bstride][kin] -> [B][kout]
+// general form: candidates [G][Bstride][kin] -> out[b * out_stride + 0..kout) (out_stride <= 0: kout)
 cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
-                            float* out_s, int64_t* out_r, cudaStream_t st);
+                            float* out_s, int64_t* out_r, cudaStream_t st, int out_stride = 0);
 // exact top-k (k <= 1024) of materialised scores [B][n] -> [B][k]; workspace: see select_workspace_bytes
 size_t select_workspace_bytes(int B);
 cudaError_t launch_select(const float* scores, int64_t n, int B, int k, int64_t row_base, int64_t row_stride, void* workspace,

@@ -305,7 +305,7 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P) {
 // candidates: [G][Bstride][kin]; output [B][kout] (kout <= kin)
 __global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ cs, const int64_t* __restrict__ cr, int G,
                                                      int Bstride, int kin, int kout, int P, float* __restrict__ out_s,
-                                                     int64_t* __restrict__ out_r) {
+                                                     int64_t* __restrict__ out_r, int out_stride) {
   extern __shared__ __align__(16) uint64_t keys[];
   const int b = blockIdx.x;
   const int C = G * kin;
@@ -330,14 +330,15 @@ __global__ void __launch_bounds__(1024) merge_kernel(const float* __restrict__ c
       s = key_score((uint32_t)(key >> 32));
       r = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
     }
-    out_s[(size_t)b * kout + e] = s;
-    out_r[(size_t)b * kout + e] = r;
+    out_s[(size_t)b * out_stride + e] = s;
+    out_r[(size_t)b * out_stride + e] = r;
   }
 }
 
 cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstride, int B, int kin, int kout,
-                            float* out_s, int64_t* out_r, cudaStream_t st) {
+                            float* out_s, int64_t* out_r, cudaStream_t st, int out_stride) {
   if (G <= 0 || B <= 0 || kin <= 0 || kout <= 0 || kout > kin || Bstride < B) return cudaErrorInvalidValue;
+  if (out_stride <= 0) out_stride = kout;
   int P = 2;
   while (P < G * kin) P <<= 1;
   if (P > 16384) return cudaErrorInvalidValue;
@@ -349,7 +350,7 @@ cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstri
     attr_set = true;
   }
   const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
-  merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, Bstride, kin, kout, P, out_s, out_r);
+  merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, Bstride, kin, kout, P, out_s, out_r, out_stride);
   count_launch();
   return cudaGetLastError();
 }

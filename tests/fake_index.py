@@ -73,6 +73,17 @@ class FakeIndex:
         q = np.stack([O.blend(img[i], txt[i], float(w[i])) for i in range(img.shape[0])])
         return self.query(q, k, require_bits, mode)
 
+    def blend_dev(self, img, txt, w, out=None, stream=None):
+        import torch
+        a, t, ww = img.cpu().numpy(), txt.cpu().numpy(), w.cpu().numpy()
+        return torch.from_numpy(np.stack([O.blend(a[i], t[i], float(ww[i])) for i in range(a.shape[0])]).astype(np.float32))
+
+    def apply_filter_sweep(self, prompt, tau, bit):
+        m = O.filter_mask(np.asarray(prompt, np.float32).reshape(1, self.dim), self.X, tau)[0]
+        for r, hit in enumerate(m.tolist()):
+            self.bits[r] = (self.bits[r] - {bit}) | ({bit} if hit else set())
+        return int(m.sum())
+
     def filter_words(self):
         return (len(self) + 255) // 256 * 8
 

@@ -124,6 +124,16 @@ def main():
             col.update(ids=[ids[4]], metadatas=[{"filter_results_json": '{"is it red?": "no"}'}])
         same(n_results=10, include=["metadatas", "distances"])
         same(n_results=10, include=["distances"], where_filters=["is it red?"], filter_mode="pre")
+        # configs 4 / 5 and the multimodal blend on the sharded collection (every rank's device does its part)
+        P = np.random.default_rng(77).standard_normal((3, d)).astype(np.float32)
+        np.testing.assert_array_equal(many.filter_sweep(P, 0.08), one.filter_sweep(P, 0.08))
+        for col in (one, many):
+            assert col.apply_filter_sweep("like P2", P[2], 0.08) == int(one.filter_sweep(P[2:3], 0.08).sum())
+        same(n_results=10, include=["metadatas", "distances"], where_filters=["like P2"], filter_mode="pre")
+        a = one.query_multimodal(Q[:3], Q[3:6], [0.2, 0.5, 0.8], n_results=10, include=["distances"])
+        b = many.query_multimodal(Q[:3], Q[3:6], [0.2, 0.5, 0.8], n_results=10, include=["distances"])
+        assert a["ids"] == b["ids"]
+        assert set(many.find_duplicates(0.95)) == set(one.find_duplicates(0.95)) and len(one.find_duplicates(0.95)) >= 1
         assert ix_err(sh) == 0
         many.close()
         one.close()

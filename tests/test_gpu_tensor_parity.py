@@ -147,3 +147,45 @@ def test_dedup_matches_oracle(gpu, n, d):
     parts = [ix.dedup(tau, row_lo=lo, row_hi=min(n, lo + 3000)) for lo in range(0, n, 3000)]
     assert sum(len(p[0]) for p in parts) == len(i)
     ix.close()
+
+
+@pytest.mark.parametrize("n,d,B,k", [(30000, 512, 40, 50), (30000, 512, 100, 100), (9000, 768, 20, 128), (20000, 256, 17, 33),
+                                     (90, 512, 16, 64),          # fewer rows than k: the later rounds run out of rows
+                                     (50000, 512, 1100, 10),     # 9 query blocks: two A groups of 8 share each corpus slice
+                                     (20000, 512, 2100, 10)])
+def test_tensor_topk_rounds_and_a_groups(gpu, n, d, B, k):
+    """32 < k <= 128 on the tensor path = ceil(k/32) exact rounds (round r only admits rows ranking after the last
+    entry of round r-1), incl. duplicate rows whose tie is cut by the row number across a round boundary; B above
+    one cluster's 1024 queries = several A groups per corpus slice in ONE launch."""
+    rng = np.random.default_rng(n + d + B + k)
+    X = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    if n > 1000:
+        X[5000:5040] = Q[0] * 0.7                                 # 40 exact duplicates straddle the 32-entry round boundary
+        X[7000:7100:2] = Q[1] * 1.3
+    ix = gpu.DeviceIndex(d, "bf16")
+    ix.add(X)
+    s, r = ix.query(Q, k, mode="tensor")
+    assert ix.last_query_path == "tensor"
+    _check_topk(s, r, Q, X, k)
+    if n > 1000:
+        assert r[0][:40].tolist() == list(range(5000, 5040))      # ties in ascending row order, across rounds
+        assert (np.diff(s, axis=1) <= 0).all()
+    s2, r2 = ix.query(Q[:16], k, mode="auto")                      # auto: B >= 16 and k <= 128 -> tensor path
+    assert ix.last_query_path == "tensor"
+    np.testing.assert_array_equal(r2, r[:16])
+    ix.close()
+
+
+def test_tensor_rounds_with_pre_filter(gpu):
+    rng = np.random.default_rng(4)
+    n, d, B, k = 20000, 512, 24, 70
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    ix = gpu.DeviceIndex(d, "bf16")
+    ix.add(X)
+    keep = rng.random(n) < 0.3
+    ix.set_filter_bits_range(0, [[3] if kp else [] for kp in keep])
+    s, r = ix.query(Q, k, require_bits=[3], mode="tensor")
+    _check_topk(s, r, Q, X, k, valid=keep)
+    ix.close()

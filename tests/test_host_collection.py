@@ -324,3 +324,118 @@ def test_micro_batcher_propagates_errors():
     mb.close()
     with pytest.raises(RuntimeError):
         mb.query(np.zeros(16, np.float32), 1)
+
+
+def test_snapshot_plus_log_format_and_compaction(tmp_path):
+    """raw row slab + ids + metadata JSONL snapshot, operation log since, compaction on checkpoint
+    (the store the reference reopens at backend/app/utils.py:109-123 and walks at main.py:522-579)."""
+    client = mmiss_b200.PersistentClient(path=str(tmp_path), dtype="f32")
+    col = client.create_collection("c", metadata={"hnsw:space": "cosine"})
+    X = _vecs(50, 8)
+    ids = [f"i{i}" for i in range(50)]
+    col.add(ids=ids, embeddings=X, metadatas=[{"n": i} for i in range(50)], documents=[f"d{i}" for i in range(50)])
+    col.delete(ids=ids[10:30])
+    d = os.path.join(str(tmp_path), "c")
+    assert os.path.getsize(os.path.join(d, "oplog.0.vec")) == 50 * 8 * 4          # the log still holds the deleted rows
+    col.persist()                                                                  # checkpoint: generation 1, compacted
+    info = json.load(open(os.path.join(d, "collection.json")))
+    assert info["gen"] == 1 and info["count"] == 30 and info["dim"] == 8 and info["format"] == C.FORMAT_VERSION
+    assert os.path.getsize(os.path.join(d, "rows.1.bin")) == 30 * 8 * 4           # deleted rows are gone from disk
+    assert not os.path.exists(os.path.join(d, "oplog.0.vec")) and os.path.getsize(os.path.join(d, "oplog.1.jsonl")) == 0
+    assert open(os.path.join(d, "ids.1.txt")).read().split("\n")[:30] == col.get(include=[])["ids"]
+    col.add(ids=["late"], embeddings=X[:1] * 2.0, metadatas=[{"n": -1}])           # lands in the new log
+    col.update(ids=["i3"], metadatas=[{"k": "v"}])
+    want = col.query(query_embeddings=X[:4], n_results=5, include=["metadatas", "documents", "distances"])
+    col._log.close(); col._vec.close(); col._log = None                            # crash: no close(), no checkpoint
+    col2 = mmiss_b200.PersistentClient(path=str(tmp_path)).get_collection("c")     # snapshot upload + log replay
+    assert col2.count() == 31
+    assert isinstance(col2._metas[0], bytes)                                       # metadata lines stay unparsed until read
+    got = col2.query(query_embeddings=X[:4], n_results=5, include=["metadatas", "documents", "distances"])
+    assert got["ids"] == want["ids"] and got["metadatas"] == want["metadatas"] and got["documents"] == want["documents"]
+    np.testing.assert_allclose(got["distances"], want["distances"], atol=1e-7)
+    assert col2.get(ids=["i3"])["metadatas"][0] == {"n": 3, "k": "v"}
+    col2.close()                                                                   # folds the log: generation 2
+    assert json.load(open(os.path.join(d, "collection.json")))["gen"] == 2
+
+
+def test_torn_log_tail_and_orphan_vectors_are_ignored(tmp_path):
+    """a crash between the vector write and its log line must not shift later embeddings."""
+    client = mmiss_b200.PersistentClient(path=str(tmp_path), dtype="f32")
+    col = client.create_collection("c")
+    X = _vecs(5, 8)
+    col.add(ids=["a", "b"], embeddings=X[:2])
+    col.add(ids=["c"], embeddings=X[2:3])
+    col._log.flush(); col._vec.flush()
+    d = os.path.join(str(tmp_path), "c")
+    with open(os.path.join(d, "oplog.0.vec"), "ab") as f:                          # orphan vector: its record never made it
+        f.write(X[3].tobytes())
+    with open(os.path.join(d, "oplog.0.jsonl"), "ab") as f:                        # torn record
+        f.write(b'{"op":"add","ids":["d"],"off":96,"nby')
+    col._log.close(); col._vec.close(); col._log = None
+    col2 = mmiss_b200.PersistentClient(path=str(tmp_path)).get_collection("c")
+    assert col2.get(include=[])["ids"] == ["a", "b", "c"]
+    assert os.path.getsize(os.path.join(d, "oplog.0.vec")) == 3 * 8 * 4            # truncated back to a clean boundary
+    col2.add(ids=["e"], embeddings=X[4:5])                                         # appends after the clean boundary
+    col2._log.close(); col2._vec.close(); col2._log = None
+    col3 = mmiss_b200.PersistentClient(path=str(tmp_path)).get_collection("c")
+    assert col3.get(include=[])["ids"] == ["a", "b", "c", "e"]
+    np.testing.assert_allclose(col3.get(ids=["e"], include=["embeddings"])["embeddings"][0], X[4])
+
+
+def test_bulk_delete_and_reset_match_sequential_semantics():
+    """collection.delete(ids=all_ids) (backend/app/main.py:1065-1069) and arbitrary bulk deletes keep ids,
+    metadata and device rows aligned."""
+    col = _coll()
+    X = _vecs(200, 8)
+    ids = [f"i{i}" for i in range(200)]
+    col.add(ids=ids, embeddings=X, metadatas=[{"n": i} for i in range(200)])
+    gone = [ids[i] for i in (0, 5, 6, 7, 150, 198, 199, 42)] + ["nope"]
+    col.delete(ids=gone)
+    assert col.count() == 192
+    for i in (1, 8, 100, 197):
+        res = col.query(query_embeddings=[X[i]], n_results=1, include=["metadatas", "distances"])
+        assert res["ids"][0] == [ids[i]] and res["metadatas"][0][0] == {"n": i} and abs(res["distances"][0][0]) < 1e-6
+    assert col.get(ids=["i5"])["ids"] == []
+    svc = mmiss_b200.SearchService(col)
+    assert svc.reset_system() and col.count() == 0
+    col.add(ids=["x"], embeddings=X[:1])
+    assert col.query(query_embeddings=X[:1], n_results=3)["ids"] == [["x"]]
+
+
+def test_filter_sweep_answers_are_lazy_and_follow_the_progress_contract(tmp_path):
+    """process_filter_on_all_images (main.py:939-1056) on CLIP embeddings: answers land in the
+    rows' filter bits, `filter_results_json` is materialised on read, progress dict has the reference's shape."""
+    client = mmiss_b200.PersistentClient(path=str(tmp_path), dtype="f32")
+    col = client.create_collection("c")
+    X = _vecs(40, 8)
+    ids = [f"i{i}" for i in range(40)]
+    col.add(ids=ids, embeddings=X, metadatas=[{"n": i, "filter_results_json": json.dumps({"old": "yes" if i % 2 else "no"})}
+                                               for i in range(40)])
+    svc = mmiss_b200.SearchService(col, encoder=lambda text=None, image=None: {"text": X[3:4]})
+    assert svc.get_filter_progress("is it X3?") == {"status": "not_found"}
+    svc.process_filter_on_all_images("is it X3?", tau=0.5)
+    prog = svc.get_filter_progress("is it X3?")
+    assert prog["status"] == "completed" and prog["progress"] == 100 and prog["processed"] == prog["total"] == 40
+    mask = col.filter_sweep(X[3:4], 0.5)[0]
+    assert prog["matched"] == int(mask.sum()) >= 1
+    raw = col._metas[3]
+    assert "is it X3?" not in raw["filter_results_json"]                            # nothing was rewritten per row
+    seen = json.loads(col.get(ids=["i3"])["metadatas"][0]["filter_results_json"])
+    assert seen == {"old": "yes", "is it X3?": "yes"}
+    res = svc.route_search_text("whatever", filters=["is it X3?"], limit=0)         # the reference's post-filter sees them
+    assert sorted(r["n"] for r in res["results"]) == np.flatnonzero(mask).tolist()
+    pre = col.query(query_embeddings=X[:1], n_results=40, where_filters=["is it X3?", "old"], filter_mode="pre")
+    assert sorted(pre["ids"][0]) == sorted(ids[i] for i in np.flatnonzero(mask) if i % 2)
+    col.update(ids=["i3"], metadatas=[{"filter_results_json": json.dumps({"old": "no"})}])   # swept bit survives an update
+    assert json.loads(col.get(ids=["i3"])["metadatas"][0]["filter_results_json"]) == {"old": "no", "is it X3?": "yes"}
+    col.delete(ids=["i0", "i1"])                                                    # answers move with their rows
+    assert json.loads(col.get(ids=["i3"])["metadatas"][0]["filter_results_json"])["is it X3?"] == "yes"
+    col._log.close(); col._vec.close(); col._log = None                            # crash + replay keeps the sweep
+    col2 = mmiss_b200.PersistentClient(path=str(tmp_path)).get_collection("c")
+    assert json.loads(col2.get(ids=["i3"])["metadatas"][0]["filter_results_json"]) == {"old": "no", "is it X3?": "yes"}
+    col2.close()
+    col3 = mmiss_b200.PersistentClient(path=str(tmp_path)).get_collection("c")     # ... and so does the snapshot
+    assert json.loads(col3.get(ids=["i3"])["metadatas"][0]["filter_results_json"]) == {"old": "no", "is it X3?": "yes"}
+    bad = mmiss_b200.SearchService(col3)                                            # no encoder: the reference's error shape
+    bad.process_filter_on_all_images("other")
+    assert bad.get_filter_progress("other") == {"status": "error", "message": "Model not available", "progress": 0}

@@ -188,6 +188,15 @@ def _service_worker(rank, world, port, out):
     mm = many.query_multimodal(Q[:2], Q[2:4], 0.3, n_results=4)
     mo = one.query_multimodal(Q[:2], Q[2:4], 0.3, n_results=4)
     assert mm["ids"] == mo["ids"]
+    # config 4 / 5 on the sharded collection: shard-local sweep gathered + interleaved, triangle-split all-pairs pass
+    P = rng.standard_normal((3, 24)).astype(np.float32)
+    np.testing.assert_array_equal(many.filter_sweep(P, 0.1), one.filter_sweep(P, 0.1))
+    for col in (one, many):
+        assert col.apply_filter_sweep("like P1", P[1], 0.1) == int(one.filter_sweep(P[1:2], 0.1).sum())
+        assert col.filter_progress["like P1"]["status"] == "completed"
+    same(n_results=20, include=["metadatas", "distances"], where_filters=["like P1"], filter_mode="pre")
+    same(n_results=20, include=["metadatas", "distances"], where_filters=["like P1", "is it red?"], filter_mode="post")
+    assert many.find_duplicates(0.999) == one.find_duplicates(0.999) and len(one.find_duplicates(0.999)) == 1
     many.close()                                                               # releases the workers
     out.put("ok")
     dist.destroy_process_group()
