@@ -11,7 +11,13 @@ PARITY STATUS
   ``chromadb>=0.4.13``), which wraps hnswlib (``space="cosine"``: vectors are L2-normalised
   at insert, distance = 1 - <q^, x^>).  Neither package is installable here, the reference
   holds no tests / golden vectors for it, so **the cosine top-k itself is "parity unpinned"**:
-  it is restated from the published definition and cross-checked against float64.
+  it is restated from the published definition and cross-checked against float64.  The DEFINITION
+  (cosine distance, ascending) is pinned against two independent third-party implementations that
+  are installed -- ``scipy.spatial.distance.cdist(.., "cosine")`` and
+  ``sklearn.neighbors.NearestNeighbors(metric="cosine", algorithm="brute")`` -- through
+  ``tests/golden/make_thirdparty_golden.py`` -> ``thirdparty_golden.npz``
+  (``tests/test_oracle.py::test_cosine_definition_matches_scipy_and_sklearn``); chromadb's own
+  outputs remain unpinned.
 * The parts of the path that ARE reference source -- the multimodal blend
   (``backend/app/main.py:850-860``), the distance->similarity map (``main.py:782``,
   ``app.py:326``), the limit rule (``main.py:757``) and the post-filter predicate

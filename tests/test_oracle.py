@@ -162,3 +162,31 @@ def test_oracle_reproduces_committed_golden(tag, cd, rq):
         ok, why = O.topk_matches(GOLD[f"scores_{tag}"][b], GOLD[f"rows_{tag}"][b], full[b], int(GOLD["k"]), 2e-6)
         assert ok, why
     assert sorted(r[1][:3].tolist()) == [3, 17, 400]  # the planted ties (cos = 1)
+
+
+# ---- (4) third-party pin of the cosine-space definition (utils.py:129) ---------------------------------
+def test_cosine_definition_matches_scipy_and_sklearn():
+    """scipy.spatial.distance.cdist(..., "cosine") and sklearn NearestNeighbors(metric="cosine", brute) on the golden
+    corpus (fixtures: tests/golden/make_thirdparty_golden.py).  chromadb itself stays unpinned (not installable);
+    this pins the DEFINITION it implements against two independent implementations."""
+    tp = np.load(os.path.join(HERE, "golden", "thirdparty_golden.npz"))
+    X, Q, k = GOLD["X"], GOLD["Q"], int(GOLD["k"])
+    keep = tp["keep"]                                                     # all rows but the zero row
+    scores = O.cosine_scores(Q, X, corpus_dtype="f32")                    # [B, N] float32 cosine similarities
+    np.testing.assert_allclose(1.0 - scores[:, keep].astype(np.float64), tp["cdist_cosine"], atol=2e-6)
+    s, r = O.cosine_topk(Q, X, k, corpus_dtype="f32")
+    zero_row = int(np.setdiff1d(np.arange(X.shape[0]), keep)[0])
+    dist_of = np.full((Q.shape[0], X.shape[0]), np.inf)
+    dist_of[:, keep] = tp["cdist_cosine"]
+    for b in range(Q.shape[0]):
+        assert zero_row not in r[b]                                       # a zero row scores 0: never in these top-10s
+        np.testing.assert_allclose(1.0 - s[b].astype(np.float64), tp["sk_dist"][b], atol=2e-6)
+        # same neighbours: identical id sets, or ids whose scipy distances agree within rounding (exact ties)
+        want = tp["sk_rows"][b]
+        if set(r[b].tolist()) != set(want.tolist()):
+            np.testing.assert_allclose(np.sort(dist_of[b][r[b]]), np.sort(dist_of[b][want]), atol=2e-6)
+    # query 1 is parallel to rows 3, 17 (an exact duplicate) and 400 (2.5 x row 3): three neighbours at distance 0;
+    # sklearn orders such ties arbitrarily, the oracle (and the engine) by ascending row
+    top3 = r[1][:3].tolist()                    # (row 400's f32 score may differ from the duplicates' by one ulp)
+    assert set(top3) == {3, 17, 400} and top3.index(3) < top3.index(17) and np.abs(tp["sk_dist"][1][:3]).max() < 1e-9
+    assert set(tp["sk_rows"][1][:3].tolist()) == {3, 17, 400}
