@@ -771,18 +771,21 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
            "h2d_bytes_per_query": args.dim * 4 * G, "d2h_bytes_per_query": k * 12,
            "planted_ok": bool(ok), "first_problem": why or None, "build_s": build_s}
     if args.dtype == "bf16" and args.batch > 0:
-        B = args.batch
-        img = rng.standard_normal((B, args.dim)).astype(np.float32)
-        txt = rng.standard_normal((B, args.dim)).astype(np.float32)
-        w = rng.random(B)
-        gx.query_multimodal(img, txt, w, k, mode="tensor")
-        b0 = time.perf_counter()
-        for _ in range(3):
+        try:
+            B = args.batch
+            img = rng.standard_normal((B, args.dim)).astype(np.float32)
+            txt = rng.standard_normal((B, args.dim)).astype(np.float32)
+            w = rng.random(B)
             gx.query_multimodal(img, txt, w, k, mode="tensor")
-        bms = (time.perf_counter() - b0) / 3 * 1e3
-        out["batched_multimodal_host"] = {"workload": f"{B} (image, text, weight) triples from host memory -> blend + K2 on every GPU + "
-                                                      "exchange -> [B, k] on the host (BASELINE config 3, end to end)",
-                                          "ms_per_batch": bms, "qps": B / (bms / 1e3)}
+            b0 = time.perf_counter()
+            for _ in range(3):
+                gx.query_multimodal(img, txt, w, k, mode="tensor")
+            bms = (time.perf_counter() - b0) / 3 * 1e3
+            out["batched_multimodal_host"] = {"workload": f"{B} (image, text, weight) triples from host memory -> blend + K2 on every "
+                                                          "GPU + exchange -> [B, k] on the host (BASELINE config 3, end to end)",
+                                              "ms_per_batch": bms, "qps": B / (bms / 1e3)}
+        except Exception as e:                        # noqa: BLE001 -- keep the per-query numbers
+            out["batched_multimodal_host"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     gx.close()
     return out
 

@@ -9,7 +9,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libvecsearch_b200.so")
+# VS_BUILD_TUNING=1: a SECOND library with the VS_TC_* / VS_SCAN_* environment knobs compiled in (-DVS_TUNING),
+# used only by tools/bench_tensor.py / tools/bench_scan.py through VS_LIB_PATH.  The product library has no knobs.
+TUNING = os.environ.get("VS_BUILD_TUNING") == "1"
+OUT = os.path.join(HERE, "libvecsearch_b200_tuning.so" if TUNING else "libvecsearch_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC",]
 
@@ -39,9 +42,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "tuning" if TUNING else "product")
     os.makedirs(objdir, exist_ok=True)
-    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-DVS_TUNING"] + os.environ.get("VS_BUILD_DEFS", "").split()
+                                                          if TUNING else [])
     nvcc = _nvcc()
 
     def compile_one(src):

@@ -348,6 +348,8 @@ class Collection:
                     self._update_one(op["id"], op.get("metadata"), op.get("document"), log=False)
                 elif kind == "delete":
                     self._delete_ids(op["ids"], log=False)
+                elif kind == "clear":
+                    self._delete_ids(list(self._ids), log=False)
                 elif kind == "sweep":
                     self._replay_sweep(op)
                 good_log = f.tell()
@@ -618,7 +620,9 @@ class Collection:
                 rows = rows[offset:]
             if limit is not None:
                 rows = rows[:limit]
-            out: Dict[str, Any] = {"ids": [self._ids[r] for r in rows], "embeddings": None, "documents": None,
+            all_rows = ids is None and not offset and limit is None
+            out: Dict[str, Any] = {"ids": list(self._ids) if all_rows else [self._ids[r] for r in rows],
+                                   "embeddings": None, "documents": None,
                                    "metadatas": None, "uris": None, "data": None, "included": include}
             if "metadatas" in include:
                 out["metadatas"] = [self._meta_out(r) for r in rows]
@@ -695,12 +699,18 @@ class Collection:
             self._log_flush()
 
     def _delete_ids(self, ids: List[str], log: bool):
+        n = len(self._ids)
+        if n and len(ids) == n and ids == self._ids:     # reset_system (main.py:1065-1069): every id, in store order
+            self._index.clear()
+            self._ids, self._metas, self._docs, self._row_of = [], [], [], {}
+            if log:
+                self._log_op({"op": "clear"})
+            return
         rows = sorted({self._row_of[i] for i in ids if i in self._row_of})
         if not rows:
             return
-        n = len(self._ids)
         gone = [self._ids[r] for r in rows]
-        if len(rows) == n:                               # reset_system (main.py:1065-1069)
+        if len(rows) == n:
             self._index.clear()
             self._ids, self._metas, self._docs, self._row_of = [], [], [], {}
         elif len(rows) == 1 or not hasattr(self._index, "remove_rows"):

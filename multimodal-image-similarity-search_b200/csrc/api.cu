@@ -268,6 +268,8 @@ int query_dev_locked(vs_index* ix, const float* q_dev, int B, int k, const uint6
       a.done_seq = o.done_seq;
       o.done_armed = true;
     }
+    if (o.q_host && single_launch && B == 1 && ix->dim <= kMaxInlineQ) a.q_host = o.q_host;
+    else if (!q_dev) return fail(VS_ERR_ARG, "no device query buffer");
     const cudaError_t le = launch_scan(a, ix->sm_count, st);
     if (le != cudaSuccess) {
       o.fused = o.done_armed = false;

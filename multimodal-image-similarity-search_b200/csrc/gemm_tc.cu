@@ -47,6 +47,7 @@ constexpr int kTcBarrierBytes = 512; // mbarriers + TMEM address holder
 constexpr int kTcSmemMax = 232448; // 227 KB
 constexpr int kTcMaxBatch = 4096;  // queries / prompts per launch (the partial-list workspace is sized for it)
 constexpr int kFilterClusterCap = 8;
+constexpr int kMaxDevices = 64;
 
 enum { kModeTopK = 0, kModeFilter = 1, kModeDedup = 2 };
 
@@ -928,10 +929,15 @@ static int tc_prefetch() {
 // clusters is asked once -- neither belongs on the per-query path.
 template <int MODE, int BN, int KL, int C, int CG>
 static int prepared_clusters(const TcPlan& pl, int sm_count) {
+  // function attributes are per DEVICE: a single process may drive several GPUs (vs_group_t)
   static std::mutex mu;
-  static size_t cached_smem = 0;
-  static int cached_n = 0;
+  static size_t smem_of[kMaxDevices] = {};
+  static int n_of[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
   std::lock_guard<std::mutex> lk(mu);
+  size_t& cached_smem = smem_of[dev];
+  int& cached_n = n_of[dev];
   if (cached_smem == pl.smem && cached_n > 0) return cached_n;
   auto kern = tc_kernel<MODE, BN, KL, C, CG>;
   int n = sm_count / C;

@@ -81,6 +81,7 @@ int serve_locked(vs_group* gr, int g, unsigned s) {
   const int B = r.B, k = r.k;
   const size_t qbytes = (size_t)B * gr->dim * 4;
   const float* q = nullptr;
+  bool inline_q = false;
   if (r.blend) {
     const size_t wbytes = (size_t)B * 8, boff = (2 * qbytes + wbytes + 15) & ~(size_t)15;
     char* dst = (char*)ix->d_stage.p;   // [img | txt | w | blended], reserved at create for b_max
@@ -90,6 +91,8 @@ int serve_locked(vs_group* gr, int g, unsigned s) {
     CU(launch_blend((const float*)dst, (const float*)(dst + qbytes), (const double*)(dst + 2 * qbytes), B, gr->dim, blended,
                     ix->stream));
     q = blended;
+  } else if (B == 1 && gr->dim <= kMaxInlineQ && !r.gather && r.mode != VS_Q_TENSOR && k <= kMaxFusedK) {
+    inline_q = true;   // one request: the query rides in the scan kernel's launch packet, no H2D copy at all
   } else {
     CU(cudaMemcpyAsync(ix->d_q.p, gr->h_in, qbytes, cudaMemcpyHostToDevice, ix->stream));
     q = (const float*)ix->d_q.p;
@@ -113,7 +116,14 @@ int serve_locked(vs_group* gr, int g, unsigned s) {
     o.done_flag = gr->h_done;
     o.done_seq = s;
   }
-  int rc = sharded_query_dev_locked(ix, q, B, k, bits, r.mode, out_s, out_r, ix->stream, &o);
+  if (inline_q) {
+    o.q_host = (const float*)gr->h_in;
+    q = (const float*)ix->d_q.p;   // only dereferenced if the shard is empty / the path cannot inline (it then holds stale data:
+                                   // copy it after all so that every path stays correct)
+    if (ix->n == 0) CU(cudaMemcpyAsync(ix->d_q.p, gr->h_in, qbytes, cudaMemcpyHostToDevice, ix->stream));
+  }
+  int rc = sharded_query_dev_locked(ix, q, B, k, bits, (r.mode == VS_Q_AUTO && inline_q) ? VS_Q_SCAN : r.mode, out_s, out_r,
+                                    ix->stream, &o);
   if (rc) return rc;
   if (g == 0 && !o.done_armed) {
     // not the single-launch fused form: the last kernel of the chain wrote the mapped area; wait for it

@@ -138,6 +138,8 @@ struct QueryOpts {
   // in: host-mapped completion flags [B]; armed only on the single-launch fused scan path
   unsigned int* done_flag = nullptr;
   unsigned int done_seq = 0;
+  // in: B == 1 on the fused scan path: the query in HOST memory, shipped inside the launch packet (no H2D copy)
+  const float* q_host = nullptr;
   // out
   bool fused = false;        // the exchange was done by the scan kernel
   bool done_armed = false;   // the kernel will raise done_flag[0..B)

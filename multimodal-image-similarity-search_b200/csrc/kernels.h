@@ -66,7 +66,9 @@ struct ScanArgs {
   int early_wait = 1;        // 0 only when the previous launch on the stream was a scan and q / the rows are older than it
   unsigned int* done_flag = nullptr;   // host-mapped completion flags [B] (request/response without a stream sync)
   unsigned int done_seq = 0;
+  const float* q_host = nullptr;       // B == 1, dim <= kMaxInlineQ: the query (HOST memory) rides in the kernel parameters
 };
+constexpr int kMaxInlineQ = 1024;
 // returns cudaErrorInvalidValue when (dtype, ld_bytes) has no instantiation
 cudaError_t launch_scan(const ScanArgs& a, int sm_count, cudaStream_t st);
 int scan_rows_per_tile(int dtype, int64_t ld_bytes);

@@ -343,11 +343,14 @@ cudaError_t launch_merge_ex(const float* cs, const int64_t* cr, int G, int Bstri
   while (P < G * kin) P <<= 1;
   if (P > 16384) return cudaErrorInvalidValue;
   const size_t smem = (size_t)P * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};      // per DEVICE: a single process may drive several GPUs (vs_group_t)
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
   merge_kernel<<<B, threads, smem, st>>>(cs, cr, G, Bstride, kin, kout, P, out_s, out_r, out_stride);

@@ -19,6 +19,7 @@
 //     kernel, no score materialisation.
 // Algorithmic HBM bytes per query = n_rows * (pitch + 4).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "exchange.cuh"
@@ -72,6 +73,8 @@ struct ScanKernelParams {
   unsigned int* done_flag;   // host-mapped [B] or nullptr: done_flag[qi] = done_seq once query qi's result is written
   unsigned int done_seq;
   XchgParams xg;      // xg.G > 0: exchange the shard's result with the peers before writing it
+  int q_inline;       // 1: the (single) query travels IN the launch packet (qv) instead of through device memory
+  float qv[kMaxInlineQ];
 };
 
 // Final step of a query, executed by ONE warp holding the shard's top-k (local rows): either write
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
         const int e0 = (c * 32 + lane) * EPC;
 #pragma unroll
         for (int e = 0; e < EPC; ++e) {
-          const float v = (e0 + e < p.dim) ? __ldg(qp + e0 + e) : 0.f;
+          const float v = (e0 + e < p.dim) ? (p.q_inline ? p.qv[e0 + e] : __ldg(qp + e0 + e)) : 0.f;
           q[c][e] = v;
           ss = fmaf(v, v, ss);
         }
@@ -382,6 +385,12 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   }
   if (!a.mask) p.use_mask = 0;
   p.q = a.q;
+  p.q_inline = 0;
+  if (a.q_host != nullptr) {
+    if (a.B != 1 || a.dim > kMaxInlineQ) return cudaErrorInvalidValue;
+    p.q_inline = 1;
+    memcpy(p.qv, a.q_host, (size_t)a.dim * sizeof(float));
+  }
   p.part_s = a.part_s;
   p.part_r = a.part_r;
   p.tickets = a.tickets;
@@ -401,7 +410,8 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.xg = a.xg;
   p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
   const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;
-  // tuning knobs for A/B runs on the box (tools/bench_scan.py); the defaults are the product values
+  // the product library has no knobs; a tuning build (-DVS_TUNING, build.py) reads them for A/B runs (tools/bench_scan.py)
+#ifdef VS_TUNING
   static const int smem_budget = [] {
     const char* v = getenv("VS_SCAN_SMEM_KB");
     const int kb = v ? atoi(v) : 0;
@@ -412,6 +422,15 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
     const int c = v ? atoi(v) : 0;
     return c >= 1 && c <= 4 ? c : kCtasPerSm;
   }();
+  static const bool pdl = [] {
+    const char* v = getenv("VS_SCAN_PDL");
+    return !(v && v[0] == '0');
+  }();
+#else
+  constexpr int smem_budget = kSmemBudget;
+  constexpr int ctas_per_sm = kCtasPerSm;
+  constexpr bool pdl = true;
+#endif
   int stages = (smem_budget - fixed) / p.stage_stride;
   if (stages < 2) stages = (kSmemMax - fixed) / p.stage_stride < 3 ? (kSmemMax - fixed) / p.stage_stride : 3;  // wide rows
   if (stages > kMaxStages) stages = kMaxStages;
@@ -433,10 +452,6 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool pdl = [] {
-    const char* v = getenv("VS_SCAN_PDL");
-    return !(v && v[0] == '0');
-  }();
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   e = cudaLaunchKernelEx(&cfg, kern, p);

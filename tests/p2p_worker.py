@@ -133,7 +133,10 @@ def main():
         a = one.query_multimodal(Q[:3], Q[3:6], [0.2, 0.5, 0.8], n_results=10, include=["distances"])
         b = many.query_multimodal(Q[:3], Q[3:6], [0.2, 0.5, 0.8], n_results=10, include=["distances"])
         assert a["ids"] == b["ids"]
-        assert set(many.find_duplicates(0.95)) == set(one.find_duplicates(0.95)) and len(one.find_duplicates(0.95)) >= 1
+        for col in (one, many):                                              # plant near-duplicates of rows 10 and 11
+            col.add(ids=["dup_a", "dup_b"], embeddings=X[10:12] + 0.002 * P[:2])
+        assert set((a_, b_) for a_, b_, _ in many.find_duplicates(0.95)) == \
+            set((a_, b_) for a_, b_, _ in one.find_duplicates(0.95)) == {(ids[10], "dup_a"), (ids[11], "dup_b")}
         assert ix_err(sh) == 0
         many.close()
         one.close()

@@ -46,7 +46,7 @@ def main():
 
         def burst():
             for i in range(a.queries):
-                ix.query_dev(q[i:i + 1], a.k, out_scores=s[i:i + 1], out_rows=r[i:i + 1], mode="scan")
+                ix.query_dev(q[i:i + 1], a.k, out_scores=s[i:i + 1], out_rows=r[i:i + 1], mode="scan", pipelined=True)
 
         for _ in range(3):
             burst()

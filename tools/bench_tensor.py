@@ -58,6 +58,29 @@ def build_index(rows, dim, dev, planted=0):
     return ix
 
 
+def cublas_now(seconds=1.5):
+    """torch.matmul bf16 8192^3 back to back on THIS box right now (the way MEASURED_PEAKS.json's sustained figure was
+    taken): boxes differ by ~10 % under the power cap, so fractions against this number compare across runs."""
+    a = torch.randn((8192, 8192), device="cuda", dtype=torch.bfloat16)
+    b = torch.randn((8192, 8192), device="cuda", dtype=torch.bfloat16)
+    for _ in range(5):
+        a @ b
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    e0.record()
+    import time
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            a @ b
+        n += 20
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    return 2.0 * 8192 ** 3 * n / (e0.elapsed_time(e1) / 1e3) / 1e12
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_250_000)
@@ -68,15 +91,20 @@ def main():
     ap.add_argument("--dedup-dim", type=int, default=768)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--skip", default="")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--tag", default="")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     pk, kind = peaks()
+    cub = cublas_now()
+    knobs = {k_: v for k_, v in os.environ.items() if k_.startswith("VS_TC_") or k_ == "VS_LIB_PATH"}
 
     def report(name, ms, flops, extra):
         tf = flops / (ms / 1e3) / 1e12
-        print(json.dumps({"kernel": name, "ms": ms, "tflops": tf, "frac_burst": tf / pk["bf16_tflops"],
-                          "frac_sustained": tf / pk["bf16_tflops_sustained"], "peak_kind": kind, **extra}), flush=True)
+        print(json.dumps({"kernel": name, "tag": a.tag, "ms": ms, "tflops": tf, "frac_burst": tf / pk["bf16_tflops"],
+                          "frac_sustained": tf / pk["bf16_tflops_sustained"], "peak_kind": kind,
+                          "cublas_bf16_now_tflops": cub, "frac_of_cublas_now": tf / cub, "knobs": knobs, **extra}), flush=True)
 
     if "topk" not in a.skip or "filter" not in a.skip:
         ix = build_index(a.rows, a.dim, dev)
@@ -86,15 +114,15 @@ def main():
         txt = torch.randn((a.batch, a.dim), generator=g, device=dev)
         w = torch.rand((a.batch,), generator=g, device=dev, dtype=torch.float64)
         q = torch.empty((a.batch, a.dim), device=dev)
-        out_s = torch.empty((a.batch, 10), device=dev)
-        out_r = torch.empty((a.batch, 10), dtype=torch.int64, device=dev)
+        out_s = torch.empty((a.batch, a.k), device=dev)
+        out_r = torch.empty((a.batch, a.k), dtype=torch.int64, device=dev)
 
         def f():
             ix.blend_dev(img, txt, w, out=q)                       # multimodal blend (main.py:850-860)
-            ix.query_dev(q, 10, out_scores=out_s, out_rows=out_r, mode="tensor")
+            ix.query_dev(q, a.k, out_scores=out_s, out_rows=out_r, mode="tensor")
         ms = timed(f, a.iters)
         report("multimodal_topk_tensor", ms, 2.0 * a.batch * a.rows * a.dim,
-               {"rows": a.rows, "dim": a.dim, "batch": a.batch, "k": 10, "qps": a.batch / (ms / 1e3),
+               {"rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k, "qps": a.batch / (ms / 1e3),
                 "corpus_gb_per_s": a.rows * a.dim * 2 / (ms / 1e3) / 1e9})
     if "filter" not in a.skip:
         g = torch.Generator(device=dev).manual_seed(6)
