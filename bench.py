@@ -491,6 +491,30 @@ def run_ours(args):
         assert np.array_equal(np.asarray(e2e_res[1]), res_r.cpu().numpy()), "e2e result differs from the device-timed result"
     e2e_s = wall(e2e_step, e2e_steps)
 
+    # ---- exchange latency table (N>1): the same Q scans without any exchange / with the fused push + ONE collect per
+    #      step (the timed form) / with a full rendezvous inside every query kernel ------------------------------------
+    xl_ms = [0.0, 0.0]
+    if G > 1 and p2p:
+        def ev_ms(fn, reps=3):
+            fn()
+            barrier()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            barrier()
+            return a0.elapsed_time(a1) / reps / Q
+
+        def local_only():
+            for i in range(Q):
+                ix.query_dev(q_dev[i:i + 1], k, out_scores=cand_s[i:i + 1], out_rows=cand_r[i:i + 1], mode="scan", pipelined=True)
+
+        def rendezvous():
+            for i in range(Q):
+                ix.query_sharded_dev(q_dev[i:i + 1], k, out_scores=out_s[i:i + 1], out_rows=out_r[i:i + 1], mode="scan")
+        xl_ms = [ev_ms(local_only), ev_ms(rendezvous)]
+
     # ---- extra (not the headline): BASELINE config 3, B blended text+image queries on tcgen05 --------
     batched_ms = 0.0
     if args.dtype == "bf16" and args.batch > 0:
@@ -631,13 +655,13 @@ def run_ours(args):
     xerr = ix.exchange_error() if p2p else 0
     if xerr:
         raise SystemExit(f"bench.py: peer exchange timed out on rank {rank} (results invalid)")
-    tvals = torch.tensor([*blocks_ms, scan_ms, e2e_s, batched_ms, filter_ms, dedup_info["ms"] if dedup_info else 0.0],
+    tvals = torch.tensor([*blocks_ms, scan_ms, e2e_s, batched_ms, filter_ms, dedup_info["ms"] if dedup_info else 0.0, *xl_ms],
                          dtype=torch.float64, device=dev)
     if G > 1:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
     tl = tvals.tolist()
     nb = len(blocks_ms)
-    blocks_ms, (scan_ms, e2e_s, batched_ms, filter_ms, dedup_ms) = tl[:nb], tl[nb:]
+    blocks_ms, (scan_ms, e2e_s, batched_ms, filter_ms, dedup_ms, xl_local, xl_rdv) = tl[:nb], tl[nb:]
     ix_closed = False
 
     # ---- one request at a time through the single-process group spanning all N GPUs (rank 0 only) -----------
@@ -686,6 +710,15 @@ def run_ours(args):
             "e2e_per_query": per_query,
             "gpu_launches": int(launches), "clocks": clocks, "build_s": t_build, "exchange": exchange,
         }
+        if xl_local > 0:
+            fused = elapsed_ms / args.steps / Q
+            line["exchange_latency"] = {
+                "unit": "ms per query, device-timed, max over ranks", "queries_per_step": Q,
+                "scan_only_no_exchange": xl_local, "scan_fused_push_one_collect_per_step": fused,
+                "scan_fused_rendezvous_per_query": xl_rdv,
+                "overhead_pct_push_collect": 100.0 * (fused / xl_local - 1.0),
+                "overhead_pct_rendezvous": 100.0 * (xl_rdv / xl_local - 1.0),
+                "note": "the exchange is P2P stores + flags over NVLink from inside the scan kernel's last CTA (csrc/exchange.cuh)"}
         if batched_ms > 0:
             tf = 2.0 * args.batch * args.rows * args.dim / (batched_ms / 1e3) / 1e12
             line["batched"] = {"workload": f"{args.batch} blended text+image queries, top-{k}, tcgen05 path "

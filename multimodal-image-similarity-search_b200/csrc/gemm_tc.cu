@@ -46,6 +46,7 @@ constexpr int kInvRing = 4;          // tiles of inverse norms staged ahead of t
 constexpr int kTcBarrierBytes = 512; // mbarriers + TMEM address holder
 constexpr int kTcSmemMax = 232448; // 227 KB
 constexpr int kTcMaxBatch = 4096;  // queries / prompts per launch (the partial-list workspace is sized for it)
+constexpr int kTopkClusterCap = 2;
 constexpr int kFilterClusterCap = 8;
 constexpr int kMaxDevices = 64;
 
@@ -331,6 +332,31 @@ __device__ __forceinline__ bool tc_mask_ok(const uint64_t* mask, uint32_t row, c
   return ok;
 }
 
+// ---- filter-sweep epilogue helpers: exact `acc * inv_norm >= tau` for 32 columns in ~2.5 instructions per column ----
+// (packed f32x2 multiply = the same round-to-nearest product as the scalar FMUL the oracle's arithmetic implies, one
+//  FSETP and one predicated OR with an immediate bit; the straightforward C compiles to ~5.)
+__device__ __forceinline__ void mul_f32x2(uint32_t a0, uint32_t a1, float b0, float b1, float& d0, float& d1) {
+  asm("{\n\t.reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mul.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "r"(a0), "r"(a1), "f"(b0), "f"(b1));
+}
+template <int J>
+__device__ __forceinline__ void or_bit_if_ge(uint32_t& bits, float s, float tau) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "f"(s), "f"(tau), "n"(1u << J));
+}
+template <int J>
+__device__ __forceinline__ void threshold_bits(uint32_t& bits, const uint32_t (&acc)[32], const float (&inv)[32], float tau) {
+  float s0, s1;
+  mul_f32x2(acc[J], acc[J + 1], inv[J], inv[J + 1], s0, s1);
+  or_bit_if_ge<J>(bits, s0, tau);
+  or_bit_if_ge<J + 1>(bits, s1, tau);
+  if constexpr (J + 2 < 32) threshold_bits<J + 2>(bits, acc, inv, tau);
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel.  C = cluster size (CTAs sharing one corpus stream, one A block each)
 // ------------------------------------------------------------------------------------------
@@ -603,42 +629,81 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #else
         constexpr int n_groups = BN / 32;
 #endif
-#pragma unroll 1
-        for (int g = half; g < n_groups; g += 2) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
-          const uint32_t rg = row0 + g * 32;
-          if (MODE == kModeTopK && t - t0 < 2u) {
-            // warm-up: the pool fills within the first groups of an item; pick the bound up per group
-            int unused;
-            gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
+        if constexpr (MODE == kModeFilter) {
+          // Filter sweep: the two warps of a lane quarter take the LOWER / UPPER half of the tile's 32-column groups, so
+          // every thread ends up with BN/64 CONSECUTIVE bit words of its prompt's row and writes them with one vector
+          // store (16 B for BN = 256) instead of BN/64 scattered 4-byte stores: 4x fewer L2 write transactions.
+          // The groups are read from TMEM TWO at a time (one wait for both loads), and the accumulator buffer is handed
+          // back to the MMA issuer as soon as the LAST load has landed in registers -- before the arithmetic on it --
+          // so the next-but-one tile's MMAs are not held up by this tile's thresholding and stores.
+          constexpr int kWords = BN / 64;
+          static_assert(kWords % 2 == 0, "two groups per TMEM wait");
+          uint32_t words[kWords];
+          bool released = false;
+#pragma unroll
+          for (int gi = 0; gi < (n_groups ? kWords : 0); gi += 2) {
+            const int g = half * kWords + gi;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v0);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (g + 1) * 32, v1);
+            tmem_ld_wait();
+            if (gi + 2 >= kWords) {   // both of this warp's last groups are in registers: release the accumulator now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);
+                else mbar_arrive(&tempty[acc]);
+              }
+              released = true;
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const uint32_t rg = row0 + (g + h2) * 32;
+              const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
+              const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * kInvStride + (g + h2) * 32);
+              float inv[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 f = ip[j];
+                inv[4 * j] = f.x;
+                inv[4 * j + 1] = f.y;
+                inv[4 * j + 2] = f.z;
+                inv[4 * j + 3] = f.w;
+              }
+              uint32_t bits = 0;
+              if (h2 == 0) threshold_bits<0>(bits, v0, inv, p.tau); else threshold_bits<0>(bits, v1, inv, p.tau);
+              words[gi + h2] = bits & (nvalid >= 32u ? 0xFFFFFFFFu : ((1u << nvalid) - 1u));
+            }
           }
+          const uint32_t f = (uint32_t)ablock * kTcM + m_local;
+          if (n_groups && f < (uint32_t)p.F) {
+            uint32_t* dst = p.out_bits + (size_t)f * p.words_per_filter + row0 / 32 + half * kWords;
+            if constexpr (kWords == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(words[0], words[1]);
+          }
+          // the inverse-norm stage is released below; the accumulator already was (unless the profiling build skipped the loop)
+          __syncwarp();
+          if (lane == 0) {
+            if (!released) {
+              tc_fence_before();
+              if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);
+              else mbar_arrive(&tempty[acc]);
+            }
+            mbar_arrive(&iempty[ib]);
+          }
+        }
+        if constexpr (MODE != kModeFilter) {
+        // one 32-column group of this thread's query (already in registers)
+        auto process = [&](const uint32_t (&v)[32], const int g) {
+          const uint32_t rg = row0 + g * 32;
           const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
           const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * kInvStride + g * 32);   // staged by the producer
-          if (MODE == kModeFilter) {
-            float inv[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 f = ip[j];
-              inv[4 * j] = f.x;
-              inv[4 * j + 1] = f.y;
-              inv[4 * j + 2] = f.z;
-              inv[4 * j + 3] = f.w;
-            }
-            tmem_ld_wait();
-            uint32_t bits = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              bits |= (__uint_as_float(v[j]) * inv[j] >= p.tau && (uint32_t)j < nvalid) ? (1u << j) : 0u;
-            const uint32_t f = (uint32_t)ablock * kTcM + m_local;
-            if (f < (uint32_t)p.F) p.out_bits[(size_t)f * p.words_per_filter + rg / 32] = bits;
-          } else {
+          {
             // Fast reject on RAW accumulators: score_j = acc_j * inv_j <= max_j(acc_j) / min_j(norm_j).
             // gmin = (1 - 2^-20) * min norm of the 32 rows, so `max acc <= bound * gmin` proves that no
             // row of the group reaches `bound`; one max tree + one warp vote per 32 rows.  The exact
             // arithmetic (acc * inv_norm, as the oracle) only runs in the rare slow path.
             const float gmn = s_invt[ib * kInvStride + BN + g];
-            tmem_ld_wait();
             float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
             for (int j = 2; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
@@ -670,6 +735,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 bool c;
                 if (MODE == kModeTopK) {
                   c = sc[j] > thr0 && sc[j] >= gb;
+                  // a later round of 32 < k <= 128: only rows ranking strictly after the previous round's last entry
+                  if (has_ub) c = c && (sc[j] < ub_s || (sc[j] == ub_s && grow0 + (int64_t)j * p.row_stride > ub_r));
                 } else {
                   sc[j] *= inv_a;
                   c = sc[j] >= p.tau && a_ok && a_global < rg + j;
@@ -712,15 +779,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           }
+        };
+        // Groups are read from TMEM kPer at a time (one tcgen05.wait::ld for the loads in flight); the accumulator buffer
+        // is handed back to the MMA issuer as soon as this warp's LAST group sits in registers, before the list work on it.
+        constexpr int kPer = (KL <= 10 && BN >= 128) ? 2 : 1;
+        bool released = false;
+        auto release_acc = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(&tempty[acc]);
+          }
+          released = true;
+        };
+#pragma unroll 1
+        for (int g = half; g < n_groups; g += 2 * kPer) {
+          uint32_t v0[32];
+          [[maybe_unused]] uint32_t v1[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v0);
+          if constexpr (kPer == 2) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (g + 2) * 32, v1);
+          if (MODE == kModeTopK && t - t0 < 2u) {
+            // warm-up: the pool fills within the first groups of an item; pick the bound up per group
+            int unused;
+            gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
+          }
+          tmem_ld_wait();
+          if (g + 2 * kPer >= n_groups) release_acc();
+          process(v0, g);
+          if constexpr (kPer == 2) process(v1, g + 2);
         }
-        // this warp is done reading the accumulator buffer
-        tc_fence_before();
+        if (!released) release_acc();
         __syncwarp();
-        if (lane == 0) {
-          if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
-          else mbar_arrive(&tempty[acc]);
-          mbar_arrive(&iempty[ib]);
-        }
+        if (lane == 0) mbar_arrive(&iempty[ib]);
+        }   // MODE != kModeFilter
       }
       if (MODE == kModeTopK) {
         // partial lists: [slice][half][Bp][KL]
@@ -1048,8 +1140,12 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
                                int64_t* out_r, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || k <= 0 || B <= 0 || !a.gmin) return cudaErrorNotSupported;
-  // K2 default: clusters of 8 when there are >= 8 query blocks (one corpus stream shared by 1024 queries)
-  static const int cap = tc_max_cluster(8);
+  // K2 default: CTA PAIRS (cluster of 2) and, for B > 256, several A groups per corpus slice: the pairs
+  // (slice, 0..n_agroups-1) sit on neighbouring SMs and stream the same tiles in lockstep, so the slice comes from HBM
+  // once and from L2 for the other groups.  74 pairs fill all 148 SMs, where clusters of 8 only fit 15 times (120 SMs):
+  // 1.25M x 512, B = 1024: 1.019 ms vs 1.104 ms (cluster 8) vs 1.068 (cluster 4); 10M rows: 8.45 vs 8.47 vs 8.72 ms
+  // (power-capped) -- profiles/r02_tensor_path.md.
+  static const int cap = tc_max_cluster(kTopkClusterCap);
   for (int b0 = 0; b0 < B; b0 += kTcMaxBatch) {
     const int nb = B - b0 < kTcMaxBatch ? B - b0 : kTcMaxBatch;
     const int Bp = (nb + kTcM - 1) / kTcM * kTcM;

@@ -169,7 +169,7 @@ def test_tensor_topk_rounds_and_a_groups(gpu, n, d, B, k):
     assert ix.last_query_path == "tensor"
     _check_topk(s, r, Q, X, k)
     if n > 1000:
-        assert r[0][:40].tolist() == list(range(5000, 5040))      # ties in ascending row order, across rounds
+        assert r[0][:min(40, k)].tolist() == list(range(5000, 5000 + min(40, k)))      # ties in ascending row order, across rounds
         assert (np.diff(s, axis=1) <= 0).all()
     s2, r2 = ix.query(Q[:16], k, mode="auto")                      # auto: B >= 16 and k <= 128 -> tensor path
     assert ix.last_query_path == "tensor"

@@ -25,17 +25,27 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def timed(fn, iters):
+def timed(fn, iters, min_seconds=0.3):
+    """ms per call: >= `iters` calls and >= `min_seconds` of device time, after a warm-up of the same length (a few
+    milliseconds are not enough for the clocks / the power governor to settle)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    n = max(iters, int(min_seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)) + 1) if iters > 1 else 1
+    for _ in range(n if iters > 1 else 0):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / n
 
 
 def build_index(rows, dim, dev, planted=0):
