@@ -411,6 +411,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def sustained_ms(fn, min_ms=250.0, first=5):
+        """(burst, sustained) ms per call, device-timed, same iteration count on every rank: `first` calls right after 3
+        warm-ups, then >= min_ms of back-to-back calls (the power governor needs more than a few milliseconds)."""
+        for _ in range(3):
+            fn()
+        barrier()
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(first):
+            fn()
+        a1.record()
+        barrier()
+        burst = torch.tensor([a0.elapsed_time(a1) / first], dtype=torch.float64, device=dev)
+        if G > 1:
+            dist.all_reduce(burst, op=dist.ReduceOp.MAX)
+        n = max(first, int(min_ms / max(float(burst.item()), 1e-3)) + 1)
+        for _ in range(n // 2):
+            fn()
+        barrier()
+        a0.record()
+        for _ in range(n):
+            fn()
+        a1.record()
+        barrier()
+        return float(burst.item()), a0.elapsed_time(a1) / n
+
     for _ in range(max(3, args.warmup)):
         res_s, res_r = step(False)
     barrier()
@@ -516,7 +542,7 @@ def run_ours(args):
         xl_ms = [ev_ms(local_only), ev_ms(rendezvous)]
 
     # ---- extra (not the headline): BASELINE config 3, B blended text+image queries on tcgen05 --------
-    batched_ms = 0.0
+    batched_ms = batched_burst_ms = 0.0
     if args.dtype == "bf16" and args.batch > 0:
         B = args.batch
         gb = torch.Generator(device=dev).manual_seed(4242)          # same queries on every rank
@@ -542,33 +568,16 @@ def run_ours(args):
                 dist.all_gather_into_tensor(bgr.view(-1, k), br)
                 ix.merge_dev(bgs, bgr, out_scores=bos, out_rows=bor)
 
-        for _ in range(3):
-            bstep()
-        barrier()
-        b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(5):
-            bstep()
-        b1.record()
-        barrier()
-        batched_ms = b0.elapsed_time(b1) / 5
+        batched_burst_ms, batched_ms = sustained_ms(bstep)
 
     # ---- extra: BASELINE config 4 (filter sweep) on this rank's shard -------------------------------
-    filter_ms = 0.0
+    filter_ms = filter_burst_ms = 0.0
     if args.dtype == "bf16" and args.filters > 0:
         gf = torch.Generator(device=dev).manual_seed(4343)
         prompts = torch.randn((args.filters, args.dim), generator=gf, device=dev)
         fbits = torch.zeros((args.filters, ix.filter_words()), dtype=torch.int32, device=dev)
-        for _ in range(3):
-            ix.filter_sweep_dev(prompts, 0.103, out_bits=fbits)           # ~1 % of random 512-d rows pass
-        barrier()
-        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(5):
-            ix.filter_sweep_dev(prompts, 0.103, out_bits=fbits)
-        f1.record()
-        barrier()
-        filter_ms = f0.elapsed_time(f1) / 5
+        # ~1 % of random 512-d rows pass
+        filter_burst_ms, filter_ms = sustained_ms(lambda: ix.filter_sweep_dev(prompts, 0.103, out_bits=fbits))
         del fbits
 
     # ---- extra: BASELINE config 2 (1M x 512 fp32, single-query scans) on one GPU ---------------------
@@ -720,21 +729,33 @@ def run_ours(args):
                 "overhead_pct_rendezvous": 100.0 * (xl_rdv / xl_local - 1.0),
                 "note": "the exchange is P2P stores + flags over NVLink from inside the scan kernel's last CTA (csrc/exchange.cuh)"}
         if batched_ms > 0:
-            tf = 2.0 * args.batch * args.rows * args.dim / (batched_ms / 1e3) / 1e12
+            # `ms_per_batch` keeps round 1's protocol (5 timed batches after 3 warm-ups) so the rounds compare; `sustained` is the
+            # same batch repeated back to back for >= 0.25 s, when the card has settled at its power cap
+            flop = 2.0 * args.batch * args.rows * args.dim
+            tf, tfs = flop / (batched_burst_ms / 1e3) / 1e12, flop / (batched_ms / 1e3) / 1e12
             line["batched"] = {"workload": f"{args.batch} blended text+image queries, top-{k}, tcgen05 path "
                                            f"(blend kernel + K2{(' + p2p exchange kernel' if p2p else ' + all-gather + merge') if G > 1 else ''})",
-                               "ms_per_batch": batched_ms, "qps": args.batch / (batched_ms / 1e3), "tflops": tf,
+                               "ms_per_batch": batched_burst_ms, "qps": args.batch / (batched_burst_ms / 1e3), "tflops": tf,
                                "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
-                               "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"]}
+                               "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"],
+                               "sustained": {"ms_per_batch": batched_ms, "qps": args.batch / (batched_ms / 1e3), "tflops": tfs,
+                                             "frac_of_bf16_sustained": tfs / G / peaks["bf16_tflops_sustained"],
+                                             "timing": ">= 0.25 s of back-to-back batches"}}
         if filter_ms > 0:
-            tf = 2.0 * args.filters * args.rows * args.dim / (filter_ms / 1e3) / 1e12
+            flop = 2.0 * args.filters * args.rows * args.dim
+            tf, tfs = flop / (filter_burst_ms / 1e3) / 1e12, flop / (filter_ms / 1e3) / 1e12
             fbytes = args.rows * args.dim * 2 + args.filters * args.rows / 8
             line["filter_sweep"] = {"workload": f"{args.filters} filter prompts x {args.rows} rows, cos >= 0.103 -> bit mask "
                                                 "(tcgen05, no exchange: mask rows are shard-local)",
-                                    "ms": filter_ms, "tflops": tf, "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
+                                    "ms": filter_burst_ms, "tflops": tf, "frac_of_bf16_burst": tf / G / peaks["bf16_tflops"],
                                     "frac_of_bf16_sustained": tf / G / peaks["bf16_tflops_sustained"],
-                                    "gb_per_s": fbytes / (filter_ms / 1e3) / 1e9,
-                                    "frac_of_hbm": fbytes / (filter_ms / 1e3) / 1e9 / G / peaks["hbm_gbs"]}
+                                    "gb_per_s": fbytes / (filter_burst_ms / 1e3) / 1e9,
+                                    "frac_of_hbm": fbytes / (filter_burst_ms / 1e3) / 1e9 / G / peaks["hbm_gbs"],
+                                    "sustained": {"ms": filter_ms, "tflops": tfs,
+                                                  "frac_of_bf16_sustained": tfs / G / peaks["bf16_tflops_sustained"],
+                                                  "frac_of_hbm": fbytes / (filter_ms / 1e3) / 1e9 / G / peaks["hbm_gbs"],
+                                                  "timing": ">= 0.25 s of back-to-back sweeps (both HBM and the tensor pipe loaded: "
+                                                            "the card sits at its power cap)"}}
         if f32_info:
             line["f32_1m"] = f32_info
         if dedup_info:

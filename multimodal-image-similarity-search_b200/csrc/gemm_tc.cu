@@ -46,7 +46,7 @@ constexpr int kInvRing = 4;          // tiles of inverse norms staged ahead of t
 constexpr int kTcBarrierBytes = 512; // mbarriers + TMEM address holder
 constexpr int kTcSmemMax = 232448; // 227 KB
 constexpr int kTcMaxBatch = 4096;  // queries / prompts per launch (the partial-list workspace is sized for it)
-constexpr int kTopkClusterCap = 2;
+constexpr int64_t kTopkPairRowsBelow = 7000000;   // shards shorter than this run K2 as CTA pairs + A groups
 constexpr int kFilterClusterCap = 8;
 constexpr int kMaxDevices = 64;
 
@@ -693,9 +693,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
         }
         if constexpr (MODE != kModeFilter) {
-        // one 32-column group of this thread's query (already in registers)
-        auto process = [&](const uint32_t (&v)[32], const int g) {
+        // (Reading two groups per tcgen05.wait::ld and releasing the accumulator before the list work -- what the filter
+        //  epilogue does -- was measured here as well: K2 lost 1 % at 10M rows and 5 % on a 1.25M-row shard under
+        //  sustained load, profiles/r02_tensor_path.md; the compact single-group loop stays.)
+#pragma unroll 1
+        for (int g = half; g < n_groups; g += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v);
           const uint32_t rg = row0 + g * 32;
+          if (MODE == kModeTopK && t - t0 < 2u) {
+            // warm-up: the pool fills within the first groups of an item; pick the bound up per group
+            int unused;
+            gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
+          }
           const uint32_t nvalid = rg < p.n_rows ? min(32u, p.n_rows - rg) : 0u;
           const float4* ip = reinterpret_cast<const float4*>(s_invt + ib * kInvStride + g * 32);   // staged by the producer
           {
@@ -704,6 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // row of the group reaches `bound`; one max tree + one warp vote per 32 rows.  The exact
             // arithmetic (acc * inv_norm, as the oracle) only runs in the rare slow path.
             const float gmn = s_invt[ib * kInvStride + BN + g];
+            tmem_ld_wait();
             float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
             for (int j = 2; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
@@ -729,14 +740,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
               }
               const float thr0 = top.threshold();
-              [[maybe_unused]] const int64_t grow0 = (int64_t)rg * p.row_stride + p.row_base;   // reported row of column 0
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 bool c;
                 if (MODE == kModeTopK) {
                   c = sc[j] > thr0 && sc[j] >= gb;
-                  // a later round of 32 < k <= 128: only rows ranking strictly after the previous round's last entry
-                  if (has_ub) c = c && (sc[j] < ub_s || (sc[j] == ub_s && grow0 + (int64_t)j * p.row_stride > ub_r));
                 } else {
                   sc[j] *= inv_a;
                   c = sc[j] >= p.tau && a_ok && a_global < rg + j;
@@ -761,7 +769,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   const float s = (j & 1) ? t2[1] : t2[0];
                   const uint32_t row = rg + j;
                   if (MODE == kModeTopK) {
-                    if (s > top.threshold()) {
+                    // (a later round of 32 < k <= 128 only admits rows ranking strictly after the previous round's last entry)
+                    if (s > top.threshold() &&
+                        (!has_ub || s < ub_s || (s == ub_s && (int64_t)row * p.row_stride + p.row_base > ub_r))) {
                       if (!p.use_mask || tc_mask_ok(p.mask, row, p.req)) {
                         top.insert(s, row);
                         atomicMax(gb_ptr + row % (uint32_t)p.k_real, score_key(s));
@@ -779,39 +789,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           }
-        };
-        // Groups are read from TMEM kPer at a time (one tcgen05.wait::ld for the loads in flight); the accumulator buffer
-        // is handed back to the MMA issuer as soon as this warp's LAST group sits in registers, before the list work on it.
-        constexpr int kPer = (KL <= 10 && BN >= 128) ? 2 : 1;
-        bool released = false;
-        auto release_acc = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
-            else mbar_arrive(&tempty[acc]);
-          }
-          released = true;
-        };
-#pragma unroll 1
-        for (int g = half; g < n_groups; g += 2 * kPer) {
-          uint32_t v0[32];
-          [[maybe_unused]] uint32_t v1[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 32, v0);
-          if constexpr (kPer == 2) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (g + 2) * 32, v1);
-          if (MODE == kModeTopK && t - t0 < 2u) {
-            // warm-up: the pool fills within the first groups of an item; pick the bound up per group
-            int unused;
-            gb = fmaxf(gb, key_score(pool_min<pool_stride(KL)>(gb_ptr, p.k_real, unused)));
-          }
-          tmem_ld_wait();
-          if (g + 2 * kPer >= n_groups) release_acc();
-          process(v0, g);
-          if constexpr (kPer == 2) process(v1, g + 2);
         }
-        if (!released) release_acc();
+        // this warp is done reading the accumulator buffer
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&iempty[ib]);
+        if (lane == 0) {
+          if (CG == 2 && !leader) mbar_arrive_cluster(&tempty[acc], rank - 1u);   // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(&tempty[acc]);
+          mbar_arrive(&iempty[ib]);
+        }
         }   // MODE != kModeFilter
       }
       if (MODE == kModeTopK) {
@@ -913,7 +899,7 @@ static int tc_block_n() {
 // largest cluster size allowed (1, 2, 4 or 8)
 static int tc_max_cluster(int dflt) {
   const int v = env_int("VS_TC_CLUSTER", dflt);
-  return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1;
+  return v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : v >= 1 ? 1 : 0;
 }
 
 struct TcPlan {
@@ -1140,12 +1126,15 @@ cudaError_t launch_tensor_topk(const TensorArgs& a, const float* q, int B, int k
                                int64_t* out_r, int sm_count, cudaStream_t st) {
   const TcPlan pl = plan_for(a.dim);
   if (!pl.ok || !dims_ok(a) || k > kMaxTensorK || k <= 0 || B <= 0 || !a.gmin) return cudaErrorNotSupported;
-  // K2 default: CTA PAIRS (cluster of 2) and, for B > 256, several A groups per corpus slice: the pairs
-  // (slice, 0..n_agroups-1) sit on neighbouring SMs and stream the same tiles in lockstep, so the slice comes from HBM
-  // once and from L2 for the other groups.  74 pairs fill all 148 SMs, where clusters of 8 only fit 15 times (120 SMs):
-  // 1.25M x 512, B = 1024: 1.019 ms vs 1.104 ms (cluster 8) vs 1.068 (cluster 4); 10M rows: 8.45 vs 8.47 vs 8.72 ms
-  // (power-capped) -- profiles/r02_tensor_path.md.
-  static const int cap = tc_max_cluster(kTopkClusterCap);
+  // Cluster choice for K2 (profiles/r02_tensor_path.md, same-box A/B under sustained load):
+  //  * clusters of 8 (one corpus stream multicast to 8 query blocks) move every tile L2->SM once per 1024 queries: the
+  //    most energy-efficient form, best on long shards where the card sits at its power cap (10M rows: 9.45 ms vs 9.99);
+  //  * CTA PAIRS with several A groups per corpus slice (the pairs (slice, 0..n_agroups-1) sit on neighbouring SMs and
+  //    stream the same tiles in lockstep: HBM once, L2 for the other groups) fill all 148 SMs where clusters of 8 only fit
+  //    15 times (120 SMs): best on shorter shards (sustained, same box: 1.25M rows 1.191 vs 1.256 ms, 2.5M 2.332 vs 2.460,
+  //    5M 4.691 vs 4.809; at 10M rows the A groups of a slice drift apart and the re-reads reach HBM: 10.30 vs 9.53 ms).
+  static const int cap_env = tc_max_cluster(0);
+  const int cap = cap_env > 0 ? cap_env : (a.n_rows >= kTopkPairRowsBelow ? 8 : 2);
   for (int b0 = 0; b0 < B; b0 += kTcMaxBatch) {
     const int nb = B - b0 < kTcMaxBatch ? B - b0 : kTcMaxBatch;
     const int Bp = (nb + kTcM - 1) / kTcM * kTcM;
