@@ -810,19 +810,26 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
         gx.query(qs[i:i + 1], k, mode="scan")
     nq = args.group_queries
     lat = np.empty(nq)
+    tl = np.empty((nq, 4))
     w0 = time.perf_counter()
     for i in range(nq):
         a = time.perf_counter()
         gx.query(qs[i % 256:i % 256 + 1], k, mode="scan")
         lat[i] = time.perf_counter() - a
+        tl[i] = gx.last_timing_us()
     wall = time.perf_counter() - w0
+    tlm = np.median(tl, axis=0)
     out = {"value": nq / wall, "unit": "queries/s", "n_gpus": G, "queries": nq,
            "latency_us": {"p50": float(np.percentile(lat, 50) * 1e6), "p99": float(np.percentile(lat, 99) * 1e6),
                           "min": float(lat.min() * 1e6)},
            "path": f"GroupIndex.query -> vs_group_query_host: ONE process, {G} GPU(s), one request at a time; query through a pinned "
                    "host-mapped area, one fused scan launch per GPU (exchange over NVLink inside the kernel), result + flag "
                    "written to host-mapped memory by the kernel, polled by the caller (no stream synchronise)",
-           "h2d_bytes_per_query": args.dim * 4 * G, "d2h_bytes_per_query": k * 12,
+           "timeline_us_median": {"query_published": float(tlm[0]), "all_launches_enqueued": float(tlm[1]),
+                                  "completion_flag_seen": float(tlm[2]), "result_copied": float(tlm[3]),
+                                  "python_and_ctypes": float(np.median(lat) * 1e6 - tlm[3])},
+           "h2d_bytes_per_query": 0 if args.dim <= 1024 else args.dim * 4 * G,
+           "query_bytes_in_launch_packets": args.dim * 4 * G if args.dim <= 1024 else 0, "d2h_bytes_per_query": k * 12,
            "planted_ok": bool(ok), "first_problem": why or None, "build_s": build_s}
     if args.dtype == "bf16" and args.batch > 0:
         try:

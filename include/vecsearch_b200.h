@@ -251,6 +251,9 @@ int vs_group_destroy(vs_group_t* g);
 int vs_group_size(const vs_group_t* g);
 vs_index_t* vs_group_shard(vs_group_t* g, int shard);
 int64_t vs_group_count(const vs_group_t* g);
+/* Host-side timeline of the LAST vs_group_query* request, microseconds since its entry: [0] query published to the
+ * workers, [1] every worker has enqueued its launch, [2] completion flags seen, [3] result copied out (introspection). */
+int vs_group_last_timing(const vs_group_t* g, double out_us[4]);
 int vs_group_query_host(vs_group_t* g, const float* q, int B, int k, const uint64_t* require_bits, int mode,
                         float* out_scores, int64_t* out_rows);
 /* search_multimodal (backend/app/main.py:829-867) on a group: every GPU blends its own copy of the

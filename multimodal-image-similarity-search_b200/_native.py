@@ -53,6 +53,7 @@ SYMBOLS = {
     "vs_group_size": (_i, [_p]),
     "vs_group_shard": (_p, [_p, _i]),
     "vs_group_count": (_i64, [_p]),
+    "vs_group_last_timing": (_i, [_p, _p]),
     "vs_group_query_host": (_i, [_p, _p, _i, _i, _p, _i, _p, _p]),
     "vs_group_query_multimodal_host": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p]),
     "vs_set_row_base": (_i, [_p, _i64]),

@@ -16,6 +16,7 @@
 // Everything else a collection needs (add / remove / filter bits / sweep / dedup) goes through the
 // per-shard vs_index_t handles returned by vs_group_shard().
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <memory>
@@ -70,6 +71,8 @@ struct vs_group {
   std::mutex cv_mu;
   std::condition_variable cv;
   std::mutex front_mu;   // one request in flight
+  // host-side timeline of the LAST request (microseconds since its entry): introspection for bench.py / tuning
+  double t_submit_us = 0, t_enqueued_us = 0, t_done_us = 0, t_return_us = 0;
 };
 
 namespace {
@@ -220,6 +223,8 @@ void resync(vs_group* gr) {
 int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, const uint64_t* bits, int mode, int blend,
                 float* out_scores, int64_t* out_rows) {
   // caller holds front_mu
+  const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
   Request& r = gr->req;
   r.B = B;
   r.k = k;
@@ -235,6 +240,7 @@ int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, con
   unsigned s = gr->seq.load(std::memory_order_relaxed) + 1;
   if (s == 0) s = 1;
   gr->seq.store(s, std::memory_order_release);
+  gr->t_submit_us = since();
   if (gr->sleepers.load() > 0) {
     std::lock_guard<std::mutex> lk(gr->cv_mu);
     gr->cv.notify_all();
@@ -245,6 +251,7 @@ int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, con
     while (gr->acked[g].load(std::memory_order_acquire) != s) cpu_relax();
     if (gr->rc[g] != VS_OK && rc == VS_OK) rc = fail(gr->rc[g], "shard %d: %s", g, gr->err[g]);
   }
+  gr->t_enqueued_us = since();
   if (rc != VS_OK) {
     resync(gr);
     return rc;
@@ -254,6 +261,7 @@ int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, con
   for (int b = 0; b < B; ++b)
     while (done[b] != s) cpu_relax();
   std::atomic_thread_fence(std::memory_order_acquire);
+  gr->t_done_us = since();
   memcpy(out_scores, gr->h_out_s, (size_t)B * k * 4);
   memcpy(out_rows, gr->h_out_r, (size_t)B * k * 8);
   for (int g = 0; g < gr->G; ++g)
@@ -262,6 +270,7 @@ int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, con
       return fail(VS_ERR_EXCHANGE, "peer exchange timed out on shard %d of %d (a GPU never pushed its candidates within ~3 s)", g,
                   gr->G);
     }
+  gr->t_return_us = since();
   return VS_OK;
 }
 
@@ -371,6 +380,14 @@ int vs_group_destroy(vs_group_t* gr) {
 
 int vs_group_size(const vs_group_t* gr) { return gr ? gr->G : 0; }
 vs_index_t* vs_group_shard(vs_group_t* gr, int shard) { return (gr && shard >= 0 && shard < gr->G) ? gr->ix[shard] : nullptr; }
+int vs_group_last_timing(const vs_group_t* gr, double out_us[4]) {
+  if (!gr || !out_us) return fail(VS_ERR_ARG, "NULL argument");
+  out_us[0] = gr->t_submit_us;
+  out_us[1] = gr->t_enqueued_us;
+  out_us[2] = gr->t_done_us;
+  out_us[3] = gr->t_return_us;
+  return VS_OK;
+}
 int64_t vs_group_count(const vs_group_t* gr) {
   int64_t n = 0;
   if (gr)

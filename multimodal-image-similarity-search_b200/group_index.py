@@ -278,6 +278,12 @@ class GroupIndex:
     def exchange_error(self) -> int:
         return max(sh.exchange_error() for sh in self.shards)
 
+    def last_timing_us(self):
+        """Host-side timeline of the last query: (published, all launches enqueued, completion seen, returned) in us."""
+        t = (C.c_double * 4)()
+        N.check(self._lib.vs_group_last_timing(self._h, t))
+        return tuple(t)
+
     # ------------------------------------------------------------------ filter sweep (config 4)
     def filter_words(self) -> int:
         return (len(self) + 255) // 256 * 8
