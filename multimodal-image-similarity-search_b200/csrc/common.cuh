@@ -167,11 +167,108 @@ struct WarpTopK {
       }
     }
   }
+  static constexpr int kPrefetch = 12;   // candidates per lane held in registers by select_from / merge_from
+  // REPLACE this list by the top-k of `nlists` lists of k entries each (list i at src + i*stride).
+  // Selection instead of insertion: all candidates (<= 32*kPrefetch) are pulled into registers with independent loads,
+  // then k rounds of "every lane offers its best remaining candidate, two warp reductions (redux.sync max on the
+  // orderable score key, min on the row among the ties) pick the winner".  A round is ~100 instructions with a short
+  // dependency chain; the insertion form costs ~8 dependent shuffles per accepted candidate and accepts ~k*ln(n/k) of
+  // them: on the tail of a single query (per-CTA merge, last-CTA merge of 296 lists, peer exchange) that was ~16 us of
+  // a 216 us request (tools/bench_group.py, k = 10 vs k = 1).  Falls back to init + merge_from for larger inputs.
+  __device__ __forceinline__ void select_from(const volatile float* src_s, const volatile uint32_t* src_r,
+                                              int nlists, int stride, int k, int lane) {
+    const int total = nlists * k;
+    if (M != 1 || total > 32 * kPrefetch) {
+      init();
+      merge_from(src_s, src_r, nlists, stride, k, lane);
+      return;
+    }
+    const int rounds = (total + 31) >> 5;
+    float ps[kPrefetch];
+    uint32_t pr[kPrefetch];
+#pragma unroll
+    for (int i = 0; i < kPrefetch; ++i) {
+      const int c = i * 32 + lane;
+      ps[i] = VS_NEG_INF;
+      pr[i] = kEmptyRow;
+      if (i < rounds && c < total) {
+        const int li = c / k, e = c - li * k;
+        ps[i] = src_s[li * stride + e];
+        pr[i] = src_r[li * stride + e];
+      }
+    }
+    float out_s = VS_NEG_INF;
+    uint32_t out_r = kEmptyRow;
+    for (int j = 0; j < k; ++j) {
+      // this lane's best remaining candidate
+      float bs = ps[0];
+      uint32_t br = pr[0];
+#pragma unroll
+      for (int i = 1; i < kPrefetch; ++i)
+        if (i < rounds && better(ps[i], pr[i], bs, br)) {
+          bs = ps[i];
+          br = pr[i];
+        }
+      const uint32_t key = br == kEmptyRow ? 0u : score_key(bs);   // empty slots lose against everything
+      const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+      const uint32_t rmin = __reduce_min_sync(0xffffffffu, key == kmax ? br : kEmptyRow);
+      const unsigned who = __ballot_sync(0xffffffffu, key == kmax && br == rmin);
+      const int src_lane = __ffs(who) - 1;
+      const float ws = __shfl_sync(0xffffffffu, bs, src_lane);
+      if (lane == j) {
+        out_s = kmax == 0u ? VS_NEG_INF : ws;
+        out_r = kmax == 0u ? kEmptyRow : rmin;
+      }
+      const bool mine = lane == src_lane;   // retire the winner (rows are unique among the candidates)
+#pragma unroll
+      for (int i = 0; i < kPrefetch; ++i) {
+        const bool hit = mine && pr[i] == br;
+        ps[i] = hit ? VS_NEG_INF : ps[i];
+        pr[i] = hit ? kEmptyRow : pr[i];
+      }
+    }
+    s[0] = out_s;
+    r[0] = out_r;
+    refresh_threshold(k - 1);
+  }
+
   // merge `nlists` sorted lists of k entries each (list i at src + i*stride) into this list.
   // Lane-parallel prefilter against the threshold, then serial insertion of the survivors.
+  // Up to 32*kPrefetch candidates are first pulled into registers with independent loads (ONE memory round trip
+  // instead of one per 32 candidates: the last CTA of a scan merges ~37 lists per warp from L2 on the query's tail).
   __device__ __forceinline__ void merge_from(const volatile float* src_s, const volatile uint32_t* src_r,
                                              int nlists, int stride, int k, int lane) {
     const int total = nlists * k;
+    if (total > 32 && total <= 32 * kPrefetch) {
+      float ps[kPrefetch];
+      uint32_t pr[kPrefetch];
+#pragma unroll
+      for (int i = 0; i < kPrefetch; ++i) {
+        const int c = i * 32 + lane;
+        ps[i] = VS_NEG_INF;
+        pr[i] = kEmptyRow;
+        if (c < total) {
+          const int li = c / k, e = c - li * k;
+          ps[i] = src_s[li * stride + e];
+          pr[i] = src_r[li * stride + e];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kPrefetch; ++i) {
+        if (i * 32 >= total) break;
+        const float cs = ps[i];
+        const uint32_t cr = pr[i];
+        unsigned live = __ballot_sync(0xffffffffu, cr != kEmptyRow && better(cs, cr, thr_s, thr_r));
+        while (live) {
+          const int src_lane = __ffs(live) - 1;
+          live &= live - 1;
+          const float ns = __shfl_sync(0xffffffffu, cs, src_lane);
+          const uint32_t nr = __shfl_sync(0xffffffffu, cr, src_lane);
+          if (accepts(ns, nr)) insert(ns, nr, k - 1, lane);
+        }
+      }
+      return;
+    }
     for (int base = 0; base < total; base += 32) {
       const int c = base + lane;
       float cs = VS_NEG_INF;

@@ -107,7 +107,7 @@ __device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>
   }
   const volatile float* ls = reinterpret_cast<const volatile float*>(mine + L.scores_off) + (size_t)slot * x.kmax;
   const volatile uint32_t* lr = reinterpret_cast<const volatile uint32_t*>(mine + L.rows_off) + (size_t)slot * x.kmax;
-  top.merge_from(ls, lr, x.G, x.Bmax * x.kmax, k, lane);
+  top.select_from(ls, lr, x.G, x.Bmax * x.kmax, k, lane);
 }
 
 }  // namespace vs

@@ -163,6 +163,9 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   float* cand_s = reinterpret_cast<float*>(empty + kMaxStages);
   uint32_t* cand_r = reinterpret_cast<uint32_t*>(cand_s + kConsumerWarps * 32 * ML);
   __shared__ int s_is_last;
+  // a query that rides in the launch packet is staged through shared memory once per CTA: reading the constant bank
+  // with a lane-varying index costs one pass per distinct address, and every consumer warp would pay it again
+  __shared__ float s_q[kMaxInlineQ];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +180,8 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
     }
     fence_mbar_init();
   }
+  if (p.q_inline)
+    for (int e = threadIdx.x; e < p.dim; e += blockDim.x) s_q[e] = p.qv[e];
   __syncthreads();
   // PDL: the next query's kernel may start filling SMs as this grid's CTAs retire.  This kernel
   // only READS the corpus/query until the partial lists are written, so -- when the host knows that
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
         const int e0 = (c * 32 + lane) * EPC;
 #pragma unroll
         for (int e = 0; e < EPC; ++e) {
-          const float v = (e0 + e < p.dim) ? (p.q_inline ? p.qv[e0 + e] : __ldg(qp + e0 + e)) : 0.f;
+          const float v = (e0 + e < p.dim) ? (p.q_inline ? s_q[e0 + e] : __ldg(qp + e0 + e)) : 0.f;
           q[c][e] = v;
           ss = fmaf(v, v, ss);
         }
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   __syncthreads();
   const size_t pbase = ((size_t)qi * gridDim.x + blockIdx.x) * k;
   if (warp == 0) {
-    top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
+    top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);   // all warps' lists (this warp's own is list 0)
     if (gridDim.x == 1) {
       emit_result<ML>(p, top, qi, k, lane);   // single CTA: this is already the shard's answer
     } else {
@@ -333,14 +338,14 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
     top.init();
     const volatile float* gs = p.part_s + (size_t)qi * gridDim.x * k;
     const volatile uint32_t* gr = p.part_r + (size_t)qi * gridDim.x * k;
-    // warp w takes CTA lists w, w+8, ... as one strided batch (32 candidates per round)
+    // warp w takes CTA lists w, w+8, ... as one strided batch
     const int nl = ((int)gridDim.x - warp + kConsumerWarps - 1) / kConsumerWarps;
-    if (nl > 0) top.merge_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
+    if (nl > 0) top.select_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
     top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
   }
   __syncthreads();
   if (warp == 0) {
-    top.merge_from(cand_s + 32 * ML, cand_r + 32 * ML, kConsumerWarps - 1, 32 * ML, k, lane);
+    top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
     if (lane == 0) p.tickets[qi] = 0;  // ready for the next launch
     emit_result<ML>(p, top, qi, k, lane);
   }
