@@ -342,6 +342,8 @@ def run_ours(args):
 
     # ---- parity plants (before anything is timed) ----------------------------------------------
     pq, plants = parity_plan(args.rows, args.dim)
+    NP = min(PARITY_QUERIES, queries_per_step(args, G))          # (a reduced --queries run checks fewer of them)
+    pq, plants = pq[:NP], plants[:NP]
     want_scores = expected_scores(pq, plants, args.dtype)
     for order in plants:
         for g_row, v in order:
@@ -351,7 +353,7 @@ def run_ours(args):
     Q = queries_per_step(args, G)
     gq = torch.Generator(device="cpu").manual_seed(99)
     q_host = torch.nn.functional.normalize(torch.randn((Q, args.dim), generator=gq), dim=1).pin_memory()
-    q_host[:PARITY_QUERIES] = torch.from_numpy(pq)          # the step's first queries are the parity queries
+    q_host[:NP] = torch.from_numpy(pq)                      # the step's first queries are the parity queries
     q_dev = q_host.to(dev)
     k = args.k
     cand_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
@@ -442,13 +444,13 @@ def run_ours(args):
     barrier()
 
     # ---- parity check of exactly the path that is timed (and of the NCCL arm) --------------------
-    ok, why = check_planted(res_r[:PARITY_QUERIES].cpu().numpy(), res_s[:PARITY_QUERIES].cpu().numpy(), plants, want_scores, tol)
+    ok, why = check_planted(res_r[:NP].cpu().numpy(), res_s[:NP].cpu().numpy(), plants, want_scores, tol)
     eq_nccl = None
     if G > 1:
-        s2, r2 = nccl_searcher.search(q_dev[:PARITY_QUERIES], k)
+        s2, r2 = nccl_searcher.search(q_dev[:NP], k)
         torch.cuda.synchronize()
         if p2p:
-            eq_nccl = bool(torch.equal(r2, res_r[:PARITY_QUERIES]) and torch.equal(s2, res_s[:PARITY_QUERIES]))
+            eq_nccl = bool(torch.equal(r2, res_r[:NP]) and torch.equal(s2, res_s[:NP]))
         ok2, why2 = check_planted(r2.cpu().numpy(), s2.cpu().numpy(), plants, want_scores, tol)
         ok, why = ok and ok2, why or why2
         if p2p and ix.exchange_error():
@@ -456,7 +458,7 @@ def run_ours(args):
     flags = torch.tensor([1 if ok else 0, 1 if eq_nccl in (None, True) else 0], device=dev)
     if G > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    parity = {"queries": PARITY_QUERIES, "planted_rows_per_query": len(PLANT_EPS) + 2, "cross_shard_tie": True,
+    parity = {"queries": NP, "planted_rows_per_query": len(PLANT_EPS) + 2, "cross_shard_tie": True,
               "ranks_checked": G, "planted_ok": bool(flags[0].item()), "tolerance": tol,
               "p2p_eq_nccl": (bool(flags[1].item()) if (G > 1 and p2p) else None),
               "first_problem_rank0": why or None}
@@ -783,7 +785,7 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
     n = args.rows
     chunk = 1 << 19
     t0 = time.perf_counter()
-    gx = M.GroupIndex(args.dim, args.dtype, devices=list(range(G)), capacity=n, b_max=64, k_max=max(32, args.k))
+    gx = M.GroupIndex(args.dim, args.dtype, devices=list(range(G)), capacity=n, b_max=max(64, args.batch), k_max=max(32, args.k))
     for s, sh in enumerate(gx.shards):
         dv = torch.device("cuda", sh.device)
         g = torch.Generator(device=dv)

@@ -18,6 +18,7 @@
 //     CTA to finish (ticket) merges all CTA lists and writes the final [k] result: no second
 //     kernel, no score materialisation.
 // Algorithmic HBM bytes per query = n_rows * (pitch + 4).
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -28,6 +29,7 @@
 namespace vs {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxScanDevices = 64;
 // Shared memory per CTA.  Deliberately about a third of the SM: two CTAs fit on one SM, so with
 // programmatic dependent launch the NEXT query's CTAs are already resident and streaming while this
 // query's CTAs run their merge/exchange tails -- the HBM pipe never drains between queries
@@ -443,8 +445,20 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + fixed;
   auto kern = scan_topk_kernel<T, CPL, M, W, FULL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  {
+    // the dynamic-smem attribute is per (kernel, device): set it once, not on every query (one driver call less on the
+    // request path, where the worker threads of a group launch on 8 devices at the same moment)
+    static std::atomic<size_t> smem_set[kMaxScanDevices] = {};
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxScanDevices || smem_set[dev].load(std::memory_order_acquire) < smem) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < kMaxScanDevices) smem_set[dev].store(smem, std::memory_order_release);
+    }
+  }
   int gx = (a.grid_x > 0 ? a.grid_x : sm_count) * ctas_per_sm;
   if ((uint32_t)gx > p.n_tiles) gx = (int)p.n_tiles;
   if (gx < 1) gx = 1;

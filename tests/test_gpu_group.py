@@ -196,3 +196,44 @@ def test_raw_slab_roundtrip_is_bit_exact(gpu):
         np.testing.assert_array_equal(sa, sb)                          # same stored bits, same inverse norms
         a.close()
         b.close()
+
+
+def test_group_is_thread_safe_under_concurrent_queries_and_adds(gpu):
+    """The filter task runs on a worker thread while routes keep querying (backend/app/main.py:410): concurrent callers on
+    ONE group serialise on the front mutex / the shard mutexes and every answer stays exact for the rows present."""
+    import threading
+    rng = np.random.default_rng(23)
+    n0, d = 6000, 128
+    X = rng.standard_normal((n0 + 2000, d)).astype(np.float32)
+    gx = gpu.GroupIndex(d, "f32", devices=[0, 0], b_max=64, k_max=32)
+    gx.add(X[:n0])
+    errors = []
+
+    def querier(seed):
+        r = np.random.default_rng(seed)
+        try:
+            for _ in range(60):
+                i = int(r.integers(0, n0))
+                s, rows = gx.query(X[i:i + 1], 5, mode="scan")
+                if rows[0][0] != i or abs(s[0][0] - 1.0) > 1e-5:          # a stored row is its own nearest neighbour
+                    errors.append(("wrong", i, rows[0].tolist(), s[0].tolist()))
+        except Exception as e:                                             # noqa: BLE001
+            errors.append(("exc", repr(e)))
+
+    def adder():
+        try:
+            for c0 in range(n0, n0 + 2000, 250):
+                gx.add(X[c0:c0 + 250])
+        except Exception as e:                                             # noqa: BLE001
+            errors.append(("exc", repr(e)))
+
+    threads = [threading.Thread(target=querier, args=(s,)) for s in range(4)] + [threading.Thread(target=adder)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert len(gx) == n0 + 2000 and gx.exchange_error() == 0
+    s, r = gx.query(X[n0 + 1999:n0 + 2000], 3, mode="scan")
+    assert r[0][0] == n0 + 1999
+    gx.close()
