@@ -205,7 +205,9 @@ def test_group_is_thread_safe_under_concurrent_queries_and_adds(gpu):
     rng = np.random.default_rng(23)
     n0, d = 6000, 128
     X = rng.standard_normal((n0 + 2000, d)).astype(np.float32)
-    gx = gpu.GroupIndex(d, "f32", devices=[0, 0], b_max=64, k_max=32)
+    # (capacity reserved up front: with both shards on ONE GPU a slab re-allocation would synchronise the device while
+    #  the peer shard's kernel waits for this shard's push -- on distinct GPUs that is only a delay)
+    gx = gpu.GroupIndex(d, "f32", devices=[0, 0], capacity=n0 + 2000, b_max=64, k_max=32)
     gx.add(X[:n0])
     errors = []
 
