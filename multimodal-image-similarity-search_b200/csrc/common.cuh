@@ -167,7 +167,7 @@ struct WarpTopK {
       }
     }
   }
-  static constexpr int kPrefetch = 12;   // candidates per lane held in registers by select_from / merge_from
+  static constexpr int kPrefetch = 12;   // candidates per lane held in registers by select_from
   // REPLACE this list by the top-k of `nlists` lists of k entries each (list i at src + i*stride).
   // Selection instead of insertion: all candidates (<= 32*kPrefetch) are pulled into registers with independent loads,
   // then k rounds of "every lane offers its best remaining candidate, two warp reductions (redux.sync max on the
@@ -234,41 +234,9 @@ struct WarpTopK {
 
   // merge `nlists` sorted lists of k entries each (list i at src + i*stride) into this list.
   // Lane-parallel prefilter against the threshold, then serial insertion of the survivors.
-  // Up to 32*kPrefetch candidates are first pulled into registers with independent loads (ONE memory round trip
-  // instead of one per 32 candidates: the last CTA of a scan merges ~37 lists per warp from L2 on the query's tail).
   __device__ __forceinline__ void merge_from(const volatile float* src_s, const volatile uint32_t* src_r,
                                              int nlists, int stride, int k, int lane) {
     const int total = nlists * k;
-    if (total > 32 && total <= 32 * kPrefetch) {
-      float ps[kPrefetch];
-      uint32_t pr[kPrefetch];
-#pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) {
-        const int c = i * 32 + lane;
-        ps[i] = VS_NEG_INF;
-        pr[i] = kEmptyRow;
-        if (c < total) {
-          const int li = c / k, e = c - li * k;
-          ps[i] = src_s[li * stride + e];
-          pr[i] = src_r[li * stride + e];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) {
-        if (i * 32 >= total) break;
-        const float cs = ps[i];
-        const uint32_t cr = pr[i];
-        unsigned live = __ballot_sync(0xffffffffu, cr != kEmptyRow && better(cs, cr, thr_s, thr_r));
-        while (live) {
-          const int src_lane = __ffs(live) - 1;
-          live &= live - 1;
-          const float ns = __shfl_sync(0xffffffffu, cs, src_lane);
-          const uint32_t nr = __shfl_sync(0xffffffffu, cr, src_lane);
-          if (accepts(ns, nr)) insert(ns, nr, k - 1, lane);
-        }
-      }
-      return;
-    }
     for (int base = 0; base < total; base += 32) {
       const int c = base + lane;
       float cs = VS_NEG_INF;

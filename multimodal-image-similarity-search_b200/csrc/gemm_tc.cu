@@ -217,6 +217,29 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "memory");
   } while (!ok);
 }
+// Waits of the producer thread (stage release) and of the epilogue warps (accumulator ready) are LONG (a whole tile): a
+// suspend-time hint lets the hardware park the warp until the phase completes instead of re-issuing try_wait tens of times
+// per microsecond (ncu, round 1 code: 12.7 M producer retries + 7.3 M epilogue retries per 2.4 ms sweep), which costs issue
+// slots and, under the power cap, clock.  VS_TC_WAIT_HINT_NS = 0 compiles the plain form.
+#ifndef VS_TC_WAIT_HINT_NS
+#define VS_TC_WAIT_HINT_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+#if VS_TC_WAIT_HINT_NS > 0
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VS_TC_WAIT_HINT_NS)
+        : "memory");
+  } while (!ok);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> f32, issued by ONE thread for the CTA
@@ -490,7 +513,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // this tile's BN inverse norms -> smem (the epilogue's exact path reads them with LDS instead
             // of stalling on L2); the array is padded past n_rows, so a whole tile is always in bounds
             const uint32_t ib = ptile % kInvRing;
-            if (ptile >= (uint32_t)kInvRing) mbar_wait(&iempty[ib], (ptile / kInvRing - 1) & 1);
+            if (ptile >= (uint32_t)kInvRing) mbar_wait_long(&iempty[ib], (ptile / kInvRing - 1) & 1);
             mbar_expect_tx(&ifull[ib], BN * 4 + (p.gmin ? BN / 32 * 4 : 0));
             bulk_g2s(s_invt + ib * kInvStride, p.inv_norm + (size_t)t * BN, BN * 4, &ifull[ib], pol_keep);
             if (p.gmin) bulk_g2s(s_invt + ib * kInvStride + BN, p.gmin + (size_t)t * (BN / 32), BN / 32 * 4, &ifull[ib], pol_keep);
@@ -499,7 +522,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int st = it % p.stages;
             const uint32_t use = it / p.stages;
             if (p.prefetch > 0) prefetch_stage(idx + (uint32_t)p.prefetch);
-            if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);   // all C CTAs have consumed this stage
+            if (use > 0) mbar_wait_long(&empty[st], (use - 1) & 1);   // all C CTAs have consumed this stage
             const int row = (int)(t * BN + rank * kPartRows);
             if (CG == 2) {
               // pair mode: the LEADER's barrier counts everything both CTAs of the pair receive for this
@@ -619,7 +642,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           int unused;
           gb = key_score(pool_min<KLP>(gb_ptr, p.k_real, unused));
         }
-        mbar_wait(&tfull[acc], (tile_ctr / ACC) & 1);
+        mbar_wait_long(&tfull[acc], (tile_ctr / ACC) & 1);
         tc_fence_after();
         const uint32_t ib = tile_ctr % kInvRing;
         mbar_wait(&ifull[ib], (tile_ctr / kInvRing) & 1);

@@ -339,9 +339,20 @@ class ShardedIndex:
         return self._finish(*self._do_query(self._bcast(a, a.shape, np.float32), int(k), words))
 
     def query_dev(self, q, k: int, out_scores=None, out_rows=None, require_bits=None, mode: str = "auto", stream=None):
-        """Device-tensor flavour of :meth:`query` (the queries are re-broadcast to the other ranks)."""
-        s, r = self.query(q.detach().cpu().numpy(), k, require_bits, mode)
-        return self._torch.from_numpy(s), self._torch.from_numpy(r)
+        """Device-tensor flavour of :meth:`query`: a CUDA tensor on the communication device is broadcast to the other
+        ranks as it is (NCCL, device to device) and the result stays on the device -- nothing bounces through the host.
+        (A peer-exchange time-out then surfaces on the next call: the sticky error word, see vs_exchange_error.)"""
+        self._require_front()
+        torch = self._torch
+        t = q.detach()
+        if not t.is_cuda or self.comm_device == "cpu":
+            s, r = self.query(t.cpu().numpy(), k, require_bits, mode)
+            return torch.from_numpy(s), torch.from_numpy(r)
+        t = t.to(torch.float32).reshape(-1, self.dim).contiguous().to(self.comm_device)
+        words = _words_of(require_bits)
+        self._header("query", t.shape[0], int(k), words=words)
+        self._dist.broadcast(t, src=self._src, group=self.group)
+        return self._do_query(t, int(k), words)
 
     def query_multimodal(self, img, txt, w, k: int, require_bits=None, mode: str = "auto"):
         self._require_front()

@@ -119,6 +119,9 @@ def main():
         same(n_results=10, include=["metadatas", "distances"])
         same(n_results=10, include=["distances"], where_filters=["is it red?"], filter_mode="pre")
         same(n_results=1000, include=["distances"])                          # k > k_max: all-gather + merge path
+        qd6 = torch.from_numpy(Q[:6]).to(dev)                                # device-resident queries: broadcast over NCCL as they are
+        assert one.query(query_embeddings=qd6, n_results=10, include=["distances"])["ids"] == \
+            many.query(query_embeddings=qd6, n_results=10, include=["distances"])["ids"]
         for col in (one, many):
             col.delete(ids=[ids[3], ids[n2 - 1], ids[12_345]])
             col.update(ids=[ids[4]], metadatas=[{"filter_results_json": '{"is it red?": "no"}'}])
