@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "multimodal-image-similarity-search_b200", "libvecsearch_b200.so")
 WANT = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "UTMALDG", "UTMAPF", "UBLKCP", "SYNCS", "UTCCP", "LDS.128", "HMMA", "FFMA",
-        "ACQBULK", "MEMBAR", "ERRBAR", "RED", "ATOMG", "LDC"]
+        "FMUL2", "REDUX", "ACQBULK", "MEMBAR", "ERRBAR", "RED", "ATOMG", "LDC"]
 
 
 def main():
