@@ -50,15 +50,18 @@ METRIC = "exact top-10 cosine search QPS, 10Mx512 bf16 corpus, single-query scan
 HBM_FALLBACK_GBS = 6650.0
 
 
-def ncu_traffic_bytes(rows_local: int, dim: int, dtype: str):
+def ncu_traffic_bytes(rows_local: int, dim: int, dtype: str, field: str = "bytes"):
     """dram__bytes_read.sum + dram__bytes_write.sum per scan launch from the committed `ncu --set full`
     captures (profiles/ncu_scan_traffic.json: "rows x dim dtype" -> bytes, with the source file); None for
-    a shape that was never captured."""
+    a shape that was never captured.  field="back_to_back_read": dram bytes READ per launch in a run of back-to-back scans
+    captured without ncu's cache flush (the shard's L2-resident slice is warm: that part never reaches HBM)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_scan_traffic.json")) as f:
             table = json.load(f)
         ent = table.get(f"{rows_local}x{dim} {dtype}")
-        return float(ent["bytes"]) if ent else None
+        if not ent:
+            return None
+        return float(ent[field]) if field in ent else None
     except Exception:
         return None
 
@@ -708,11 +711,15 @@ def run_ours(args):
                          "peak": peaks["hbm_gbs"], "peak_kind": peaks_kind, "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": ncu_traffic_bytes(n_local, args.dim, args.dtype),
+                         "traffic_read_back_to_back": ncu_traffic_bytes(n_local, args.dim, args.dtype, "back_to_back_read"),
+                         "l2_resident_slice_bytes": 64 << 20,
                          "bytes_per_launch": rows_bytes, "avg_launch_ms": scan_ms,
                          "note": "peak = MEASURED_PEAKS.json hbm_gbs, a read+write COPY bandwidth; this kernel only "
                                  "reads, so frac can exceed 1 (ncu: gpu__dram_throughput ~89 % of the DRAM peak, "
                                  "profiles/); avg_launch_ms is per scan inside a burst of back-to-back launches "
-                                 "(consecutive scans overlap under PDL)"},
+                                 "(consecutive scans overlap under PDL).  traffic = one launch with a COLD L2 (ncu flushes it); "
+                                 "in a run of back-to-back queries up to 64 MB of every shard (tiles loaded evict_last) stay in "
+                                 "L2 and never reach HBM: traffic_read_back_to_back (ncu --cache-control none, single metric)"},
             "e2e": {"value": Q * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q * args.dim * 4,
                     "d2h_bytes_per_step": Q * k * 12, "steps": e2e_steps,
                     "path": ("vs_query_topk_host(B=%d, scan) via ctypes" % Q) if G == 1 else

@@ -232,6 +232,68 @@ struct WarpTopK {
     refresh_threshold(k - 1);
   }
 
+  // ---- selection over SORTED lists held in shared memory as packed keys -------------------------------------------
+  // key = score_key : ~row (64 bit, larger ranks first, 0 = empty slot).  Used on the tail of a single query, where one
+  // warp works alone and the dependent-instruction chain IS the latency (tools/scan_stamps.py: the register-scan form,
+  // select_from, cost 3.4 us per call at k = 10 -- three calls per query).
+  static __device__ __forceinline__ uint64_t pack_key(float sc, uint32_t row) {
+    return row == kEmptyRow ? 0ull : ((uint64_t)score_key(sc) << 32) | (uint32_t)~row;
+  }
+  // write the first k entries as packed keys
+  __device__ __forceinline__ void store_keys(uint64_t* dst, int k, int lane) const {
+    static_assert(M == 1, "packed-key lists are a k <= 32 form");
+    if (lane < k) dst[lane] = pack_key(s[0], r[0]);
+  }
+  // REPLACE this list by the top-k of `nlists` <= 64 sorted key lists (list i at keys + i*stride, k entries each, empties
+  // last).  Lane l owns lists l and l+32 and keeps only their current head and the entry after it in registers.  A
+  // round: max of the lane's two heads, ONE redux.sync.max on the score word, a ballot to find the owner (a second redux
+  // on the row word only when two lanes tie on the score), then the owner moves to its prefetched next entry and issues
+  // the load of the one after.  The winner reaches output lane j by a shuffle that nothing waits for.
+  static constexpr int kMaxSortedLists = 64;
+  __device__ __forceinline__ void select_sorted_smem(const uint64_t* keys, int nlists, int stride, int k, int lane) {
+    static_assert(M == 1, "packed-key lists are a k <= 32 form");
+    const uint64_t* l0 = keys + (size_t)lane * stride;
+    const uint64_t* l1 = keys + (size_t)(lane + 32) * stride;
+    const bool has0 = lane < nlists, has1 = lane + 32 < nlists;
+    int c0 = 0, c1 = 0;
+    uint64_t h0 = has0 ? l0[0] : 0ull, h1 = has1 ? l1[0] : 0ull;
+    uint64_t n0 = (has0 && k > 1) ? l0[1] : 0ull, n1 = (has1 && k > 1) ? l1[1] : 0ull;
+    uint32_t out_hi = 0u, out_lo = 0u;
+    for (int j = 0; j < k; ++j) {
+      const uint64_t m = h0 > h1 ? h0 : h1;
+      const uint32_t mhi = (uint32_t)(m >> 32), mlo = (uint32_t)m;
+      const uint32_t hi = __reduce_max_sync(0xffffffffu, mhi);
+      if (hi == 0u) break;   // every list exhausted (warp-uniform); the remaining output slots stay empty
+      bool cand = mhi == hi;
+      unsigned who = __ballot_sync(0xffffffffu, cand);
+      if (who & (who - 1u)) {   // equal scores in different lanes: the lower row (larger ~row) goes first
+        const uint32_t lo = __reduce_max_sync(0xffffffffu, cand ? mlo : 0u);
+        cand = cand && mlo == lo;
+        who = __ballot_sync(0xffffffffu, cand);   // rows are unique among the candidates: exactly one lane is left
+      }
+      const int src = __ffs(who) - 1;
+      const uint32_t wlo = __shfl_sync(0xffffffffu, mlo, src);
+      if (lane == j) {
+        out_hi = hi;
+        out_lo = wlo;
+      }
+      if (lane == src) {
+        if (h0 == m) {
+          h0 = n0;
+          ++c0;
+          n0 = c0 + 1 < k ? l0[c0 + 1] : 0ull;
+        } else {
+          h1 = n1;
+          ++c1;
+          n1 = c1 + 1 < k ? l1[c1 + 1] : 0ull;
+        }
+      }
+    }
+    s[0] = out_hi == 0u ? VS_NEG_INF : key_score(out_hi);
+    r[0] = out_hi == 0u ? kEmptyRow : ~out_lo;
+    refresh_threshold(k - 1);
+  }
+
   // merge `nlists` sorted lists of k entries each (list i at src + i*stride) into this list.
   // Lane-parallel prefilter against the threshold, then serial insertion of the survivors.
   __device__ __forceinline__ void merge_from(const volatile float* src_s, const volatile uint32_t* src_r,
@@ -257,5 +319,35 @@ struct WarpTopK {
     }
   }
 };
+
+// Copy `nl` sorted lists of k (score, row) entries from GLOBAL memory (list i at gs/gr + i*gstride) into shared memory as
+// packed keys, dst[i*k + e].  The loads of a chunk (32 lanes x kStageUnroll entries) are all issued before the first
+// store: a rolled loop would pay one L2 round trip per 32 entries (0.4 us each on the tail of a query).
+constexpr int kStageUnroll = 8;
+__device__ __forceinline__ void stage_lists_as_keys(const volatile float* gs, const volatile uint32_t* gr, int nl,
+                                                    size_t gstride, int k, uint64_t* dst, int lane) {
+  const int total = nl * k;
+  const uint32_t inv_k = ((1u << 20) + (uint32_t)k - 1u) / (uint32_t)k;   // c / k == (c * inv_k) >> 20 for c < 32768, k <= 32
+  for (int c0 = 0; c0 < total; c0 += 32 * kStageUnroll) {
+    float vs[kStageUnroll];
+    uint32_t vr[kStageUnroll];
+#pragma unroll
+    for (int u = 0; u < kStageUnroll; ++u) {
+      const int c = c0 + u * 32 + lane;
+      vs[u] = VS_NEG_INF;
+      vr[u] = kEmptyRow;
+      if (c < total) {
+        const int li = (int)(((uint32_t)c * inv_k) >> 20), e = c - li * k;
+        vs[u] = gs[(size_t)li * gstride + e];
+        vr[u] = gr[(size_t)li * gstride + e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kStageUnroll; ++u) {
+      const int c = c0 + u * 32 + lane;
+      if (c < total) dst[c] = WarpTopK<1>::pack_key(vs[u], vr[u]);
+    }
+  }
+}
 
 }  // namespace vs

@@ -77,8 +77,11 @@ __device__ __forceinline__ void xchg_push(const XchgParams& x, const WarpTopK<M>
 
 // steps 3 + 4 (warp-collective): `top` is re-initialised and receives the global top-k, or stays
 // empty when a peer never arrived (see the header comment).
+// sm_keys: optional shared-memory scratch of sm_entries 64-bit slots owned by the calling warp: the G lists are copied
+// there (packed) and selected with per-lane cursors (WarpTopK::select_sorted_smem) instead of the register scan.
 template <int M>
-__device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>& top, int slot, int k, int lane) {
+__device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>& top, int slot, int k, int lane,
+                                                uint64_t* sm_keys = nullptr, int sm_entries = 0) {
   const XchgLayout L = xchg_layout(x.Bmax, x.kmax, x.G);
   const size_t half = (size_t)(x.epoch & 1u) * L.half_bytes;
   const unsigned char* mine = x.peers[x.rank] + half;
@@ -107,6 +110,15 @@ __device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>
   }
   const volatile float* ls = reinterpret_cast<const volatile float*>(mine + L.scores_off) + (size_t)slot * x.kmax;
   const volatile uint32_t* lr = reinterpret_cast<const volatile uint32_t*>(mine + L.rows_off) + (size_t)slot * x.kmax;
+  if constexpr (M == 1) {
+    if (sm_keys != nullptr && x.G * k <= sm_entries) {
+      __syncwarp();
+      stage_lists_as_keys(ls, lr, x.G, (size_t)x.Bmax * x.kmax, k, sm_keys, lane);
+      __syncwarp();
+      top.select_sorted_smem(sm_keys, x.G, k, k, lane);
+      return;
+    }
+  }
   top.select_from(ls, lr, x.G, x.Bmax * x.kmax, k, lane);
 }
 

@@ -5,7 +5,8 @@
 // exactly once per query:
 //   * a producer thread per CTA moves tiles of R whole rows (R*pitch contiguous bytes) plus
 //     their R inverse norms into a ring of shared-memory stages with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), L2 evict_first;
+//     (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), L2 evict_first -- except a fixed ~64 MB slice of the
+//     shard that is loaded evict_last and so stays L2-resident from one query to the next (kL2KeepBytes);
 //   * 8 consumer warps read the staged rows with conflict-free 128-bit LDS, FMA against the
 //     L2-normalised query held in registers (query normalisation is fused: every warp derives
 //     1/||q|| itself), butterfly-reduce, scale by the row's inverse norm;
@@ -16,7 +17,9 @@
 //     up for rows that would enter the list -- zero extra traffic;
 //   * the per-warp lists are merged per CTA, written to a small global buffer, and the last
 //     CTA to finish (ticket) merges all CTA lists and writes the final [k] result: no second
-//     kernel, no score materialisation.
+//     kernel, no score materialisation.  For k <= 32 every merge on this tail is a cursor selection
+//     over sorted lists of packed 64-bit keys in shared memory (WarpTopK::select_sorted_smem): the
+//     tail is pure latency for an isolated request (tools/scan_stamps.py, profiles/r02_group_latency.md).
 // Algorithmic HBM bytes per query = n_rows * (pitch + 4).
 #include <atomic>
 #include <cstdlib>
@@ -37,6 +40,23 @@ constexpr int kMaxScanDevices = 64;
 constexpr int kSmemBudget = 76 * 1024;
 constexpr int kCtasPerSm = 2;
 constexpr int kSmemMax = 220 * 1024;
+// Bytes of each shard kept L2-resident across queries (evict_last tiles, see the producer loop).  0 disables.
+constexpr int64_t kL2KeepBytes = 64ll << 20;
+
+// -DVS_SCAN_STAMPS (tuning builds only, tools/scan_stamps.py): %globaltimer marks of one query's phases
+#ifdef VS_SCAN_STAMPS
+__device__ unsigned long long g_scan_stamps[8];
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VS_STAMP_MIN(i) atomicMin(&g_scan_stamps[i], gtime_ns())
+#define VS_STAMP_MAX(i) atomicMax(&g_scan_stamps[i], gtime_ns())
+#else
+#define VS_STAMP_MIN(i) ((void)0)
+#define VS_STAMP_MAX(i) ((void)0)
+#endif
 
 // rows per consumer warp per tile, chosen so a stage (W warps x U rows x pitch) is <= 32 KB
 #ifndef VS_SCAN_TILE_SHIFT
@@ -75,6 +95,7 @@ struct ScanKernelParams {
   unsigned int* done_flag;   // host-mapped [B] or nullptr: done_flag[qi] = done_seq once query qi's result is written
   unsigned int done_seq;
   XchgParams xg;      // xg.G > 0: exchange the shard's result with the peers before writing it
+  uint32_t keep_mod;  // > 0: every keep_mod-th tile of each CTA is loaded L2 evict_last (the shard's L2-resident slice)
   int q_inline;       // 1: the (single) query travels IN the launch packet (qv) instead of through device memory
   float qv[kMaxInlineQ];
 };
@@ -84,14 +105,15 @@ struct ScanKernelParams {
 // lists and write the merged GLOBAL top-k.  Exactly one warp per query reaches this point, and it
 // never waits before its own push, so ranks cannot deadlock on each other.
 template <int ML>
-__device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<ML>& top, int qi, int k, int lane) {
+__device__ __forceinline__ void emit_result(const ScanKernelParams& p, WarpTopK<ML>& top, int qi, int k, int lane,
+                                            uint64_t* sm_keys, int sm_entries) {
   if (p.xg.G > 0) {
 #pragma unroll
     for (int m = 0; m < ML; ++m)
       if (top.r[m] != kEmptyRow) top.r[m] = top.r[m] * (uint32_t)p.row_stride + (uint32_t)p.row_base;   // global rows < 2^32 (checked on the host)
     xchg_push(p.xg, top, p.xg.slot0 + qi, k, lane);
     if (p.xg.push_only) return;   // vs_exchange_collect_dev merges the whole epoch later
-    xchg_wait_merge(p.xg, top, p.xg.slot0 + qi, k, lane);
+    xchg_wait_merge(p.xg, top, p.xg.slot0 + qi, k, lane, sm_keys, sm_entries);
   }
   const int64_t add = p.xg.G > 0 ? 0 : p.row_base;
   const int64_t mul = p.xg.G > 0 ? 1 : p.row_stride;
@@ -176,24 +198,24 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   const int chunks = p.ld_bytes >> 4;
 
   if (threadIdx.x == 0) {
+    VS_STAMP_MIN(0);   // first / last CTA entering
+    VS_STAMP_MAX(1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kConsumerWarps);
     }
     fence_mbar_init();
   }
-  if (p.q_inline)
-    for (int e = threadIdx.x; e < p.dim; e += blockDim.x) s_q[e] = p.qv[e];
   __syncthreads();
   // PDL: the next query's kernel may start filling SMs as this grid's CTAs retire.  This kernel
   // only READS the corpus/query until the partial lists are written, so -- when the host knows that
   // nothing this kernel reads was produced by the grid right before it in the stream (early_wait = 0:
   // the previous launch was a scan of this library and the caller vouches for q, VS_Q_PIPELINED) --
   // the wait on the previous grid (which may still be merging into the same workspace) is deferred
-  // to that point.  Otherwise the wait comes first: the PDL contract makes the primary's writes
-  // visible only after griddepcontrol.wait.
+  // to that point.  Otherwise the wait comes first (producer: before its first load; consumers: before
+  // they read q): the PDL contract makes the primary's writes visible only after griddepcontrol.wait.
   pdl_launch_dependents();
-  if (M == 0 || p.early_wait) pdl_wait();   // (the materialising variant writes shared scratch while scanning)
+  const bool wait_first = (M == 0) || p.early_wait;   // (the materialising variant writes shared scratch while scanning)
 
   WarpTopK<ML> top;
   top.init();
@@ -201,9 +223,19 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   if (warp == kConsumerWarps) {
     // ===================== producer: one thread drives the TMA bulk pipeline ==============
     if (lane == 0) {
-      const uint64_t pol = policy_evict_first();
+      if (wait_first) pdl_wait();
+      // Everything streams evict_first EXCEPT a fixed slice of the shard (tile `it` of CTA `x` with (it + x) % keep_mod
+      // == 0, about kL2KeepBytes in total) that is loaded evict_last: a shard is many times the 126 MB L2, so without
+      // a hint nothing survives from one query to the next; with it the same ~5 % of the tiles hit in L2 on EVERY
+      // query and HBM only has to deliver the rest.  The slice is staggered over CTAs and iterations so that the hits
+      // are spread over the whole scan (L2 serves them while HBM streams the other tiles) instead of front-loaded.
+      const uint64_t pol_stream = policy_evict_first();
+      const uint64_t pol_keep = policy_evict_last();
       uint32_t it = 0;
+      uint32_t phase = p.keep_mod ? blockIdx.x % p.keep_mod : 1u;   // == (it + blockIdx.x) % keep_mod, kept incrementally
       for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const uint64_t pol = (p.keep_mod && phase == 0) ? pol_keep : pol_stream;
+        if (p.keep_mod && ++phase == p.keep_mod) phase = 0;
         const int st = it % p.stages;
         const uint32_t use = it / p.stages;
         if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
@@ -220,6 +252,13 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
     __syncwarp();
   } else {
     // ===================== consumers =======================================================
+    // a query that rides in the launch packet is staged through shared memory by the consumer warps while the
+    // producer's first tiles are already in flight (named barrier: the producer warp does not take part)
+    if (p.q_inline) {
+      for (int e = threadIdx.x; e < p.dim; e += kConsumerWarps * 32) s_q[e] = p.qv[e];
+      asm volatile("bar.sync 1, %0;" ::"r"(kConsumerWarps * 32) : "memory");
+    }
+    if (wait_first) pdl_wait();
     // normalised query in registers: chunk c*32+lane of the row <-> q elements [ch*EPC, +EPC)
     float q[CPL][EPC];
     {
@@ -248,6 +287,12 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
     for (uint32_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const int st = it % p.stages;
       mbar_wait(&full[st], (it / p.stages) & 1);
+#ifdef VS_SCAN_STAMPS
+      if (it == 0 && threadIdx.x == 0) {
+        VS_STAMP_MIN(2);   // first tile landed: earliest / latest CTA
+        VS_STAMP_MAX(3);
+      }
+#endif
       const uint8_t* tile = s_rows + (size_t)st * p.stage_stride + (size_t)(warp * U) * p.ld_bytes;
       // all LDS.128 of the warp's U rows are issued before any FMA (U*CPL loads in flight);
       // FULL = every lane owns a valid chunk in every pass, so the loads are unpredicated
@@ -310,16 +355,28 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   }
 
   if constexpr (M == 0) return;
+  if (threadIdx.x == 0) {
+    VS_STAMP_MIN(4);   // streaming done: earliest / latest CTA
+    VS_STAMP_MAX(5);
+  }
   if (!p.early_wait) pdl_wait();   // previous grid fully done: its partial lists / tickets / result rows are no longer in use
 
   // ---- per-CTA merge of the 8 warp lists ---------------------------------------------------
-  if (warp < kConsumerWarps) top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+  // k <= 32 (ML == 1): lists travel through shared memory as packed 64-bit keys and are merged by cursor selection
+  // (WarpTopK::select_sorted_smem); the candidate area [W][32] x (f32 + u32) is exactly [W][32] keys.
+  uint64_t* cand_k = reinterpret_cast<uint64_t*>(cand_s);
+  if (warp < kConsumerWarps) {
+    if constexpr (ML == 1) top.store_keys(cand_k + warp * 32, k, lane);
+    else top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+  }
   __syncthreads();
   const size_t pbase = ((size_t)qi * gridDim.x + blockIdx.x) * k;
   if (warp == 0) {
-    top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);   // all warps' lists (this warp's own is list 0)
+    // all warps' lists (this warp's own is list 0)
+    if constexpr (ML == 1) top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
+    else top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
     if (gridDim.x == 1) {
-      emit_result<ML>(p, top, qi, k, lane);   // single CTA: this is already the shard's answer
+      emit_result<ML>(p, top, qi, k, lane, cand_k, kConsumerWarps * 32 * ML);   // single CTA: this is already the shard's answer
     } else {
       top.store(p.part_s + pbase, p.part_r + pbase, k, lane);
       __threadfence();
@@ -340,16 +397,46 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
     top.init();
     const volatile float* gs = p.part_s + (size_t)qi * gridDim.x * k;
     const volatile uint32_t* gr = p.part_r + (size_t)qi * gridDim.x * k;
-    // warp w takes CTA lists w, w+8, ... as one strided batch
+    // warp w takes CTA lists w, w+8, ...
     const int nl = ((int)gridDim.x - warp + kConsumerWarps - 1) / kConsumerWarps;
-    if (nl > 0) top.select_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
-    top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+    if constexpr (ML == 1) {
+      // The lists are copied (independent, coalesced loads; packed on the way) into this warp's slice of the row ring --
+      // every tile has been consumed by now, the ring is free -- and selected there.  A slice holds `cap` lists; more
+      // than that (large k) go in batches, with the running result carried along as list 0 of the next batch.
+      const int slice_keys = (int)(((size_t)p.stages * p.stage_stride / kConsumerWarps) >> 3);
+      uint64_t* lk = reinterpret_cast<uint64_t*>(s_rows) + (size_t)warp * slice_keys;
+      int cap = slice_keys / k;
+      if (cap > WarpTopK<ML>::kMaxSortedLists) cap = WarpTopK<ML>::kMaxSortedLists;
+      int done = 0;
+      if (cap < 2) {   // (cannot happen with the shipped tile shapes: a slice is >= 64 keys) -- register-scan form
+        if (nl > 0) top.select_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
+        done = nl;
+      }
+      while (done < nl) {
+        const int carry = done > 0 ? 1 : 0;
+        const int nb = nl - done < cap - carry ? nl - done : cap - carry;
+        if (carry) top.store_keys(lk, k, lane);
+        stage_lists_as_keys(gs + ((size_t)warp + (size_t)done * kConsumerWarps) * k, gr + ((size_t)warp + (size_t)done * kConsumerWarps) * k,
+                            nb, (size_t)kConsumerWarps * k, k, lk + carry * k, lane);
+        __syncwarp();
+        top.select_sorted_smem(lk, nb + carry, k, k, lane);
+        __syncwarp();
+        done += nb;
+      }
+      top.store_keys(cand_k + warp * 32, k, lane);
+    } else {
+      if (nl > 0) top.select_from(gs + (size_t)warp * k, gr + (size_t)warp * k, nl, kConsumerWarps * k, k, lane);
+      top.store(cand_s + warp * 32 * ML, cand_r + warp * 32 * ML, k, lane);
+    }
   }
   __syncthreads();
   if (warp == 0) {
-    top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
+    if constexpr (ML == 1) top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
+    else top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
     if (lane == 0) p.tickets[qi] = 0;  // ready for the next launch
-    emit_result<ML>(p, top, qi, k, lane);
+    if (lane == 0) VS_STAMP_MAX(6);    // shard's top-k selected
+    emit_result<ML>(p, top, qi, k, lane, cand_k, kConsumerWarps * 32 * ML);
+    if (lane == 0) VS_STAMP_MAX(7);    // result (and flag) written
   }
 }
 
@@ -416,6 +503,19 @@ static cudaError_t launch_one(const ScanArgs& a, int sm_count, cudaStream_t st) 
   p.done_seq = a.done_seq;
   p.xg = a.xg;
   p.stage_stride = (int)((R * a.ld_bytes + 127) & ~127LL);
+  {
+#ifdef VS_TUNING
+    static const int64_t keep_bytes = [] {
+      const char* v = getenv("VS_SCAN_KEEP_MB");
+      return v ? (int64_t)atoi(v) << 20 : kL2KeepBytes;
+    }();
+#else
+    constexpr int64_t keep_bytes = kL2KeepBytes;
+#endif
+    const int64_t shard_bytes = a.n_rows * a.ld_bytes;
+    p.keep_mod = keep_bytes > 0 ? (uint32_t)((shard_bytes + keep_bytes - 1) / keep_bytes) : 0u;
+    if (keep_bytes > 0 && p.keep_mod < 1) p.keep_mod = 1;
+  }
   const int fixed = kMaxStages * R * 4 + 2 * kMaxStages * 8 + kConsumerWarps * 32 * ML * 8 + 256;
   // the product library has no knobs; a tuning build (-DVS_TUNING, build.py) reads them for A/B runs (tools/bench_scan.py)
 #ifdef VS_TUNING
@@ -513,3 +613,17 @@ cudaError_t launch_scan(const ScanArgs& a, int sm_count, cudaStream_t st) {
 }
 
 }  // namespace vs
+
+#ifdef VS_SCAN_STAMPS
+// tuning builds only (not part of the ABI): reset != 0 re-arms the marks on the current device, else copies them out
+extern "C" int vs_debug_scan_stamps(int reset, unsigned long long* out) {
+  unsigned long long v[8];
+  if (reset) {
+    for (int i = 0; i < 8; ++i) v[i] = (i == 0 || i == 2 || i == 4) ? ~0ull : 0ull;
+    return (int)cudaMemcpyToSymbol(vs::g_scan_stamps, v, sizeof(v));
+  }
+  const cudaError_t e = cudaMemcpyFromSymbol(v, vs::g_scan_stamps, sizeof(v));
+  if (e == cudaSuccess && out) memcpy(out, v, sizeof(v));
+  return (int)e;
+}
+#endif

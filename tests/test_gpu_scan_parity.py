@@ -89,6 +89,42 @@ def test_exact_ties_break_by_row(gpu):
     ix.close()
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("n", [40, 700, 50_000])
+def test_ties_on_the_query_tail(gpu, dtype, n):
+    """k <= 32 takes the cursor selection over packed keys (per-CTA lists, the last CTA's merge of every CTA list):
+    blocks of identical rows give equal scores in different warps, CTAs and lists -- the order must still be
+    (score desc, row asc), for one CTA (n = 40), a few (700: some warps of the last CTA get no list) and all 296."""
+    rng = np.random.default_rng(11)
+    d = 256
+    a, b, c = (rng.standard_normal(d).astype(np.float32) for _ in range(3))
+    q = a + 0.2 * b                                   # cos(q, a) ~ 0.98 > cos(q, a + b) ~ 0.83 > cos(q, b) ~ 0.2 > cos(q, c) ~ 0
+    X = np.tile(c, (n, 1))
+    idx_a = np.arange(5, n, 97)[:6]                   # copies of a, spread over the tiles
+    idx_ab = np.arange(11, n, 89)[:9]
+    idx_b = np.arange(2, n, 83)[:30]
+    X[idx_b] = b
+    X[idx_ab] = a + b
+    X[idx_a] = a
+    grp = np.full(n, 3)
+    grp[idx_b], grp[idx_ab], grp[idx_a] = 2, 1, 0
+    want = np.lexsort((np.arange(n), grp)).tolist()                # (score desc, row asc)
+    ix = gpu.DeviceIndex(d, dtype)
+    ix.add(X)
+    for k in (1, 7, 10, 32):
+        s, r = ix.query(q[None], k, mode="scan")
+        kk = min(k, n)
+        assert r[0][:kk].tolist() == want[:kk], (dtype, n, k, r[0].tolist(), want[:kk])
+        assert np.all(np.diff(s[0][:kk]) <= 0)
+    # a filter that leaves fewer rows than k: the tail must come back empty, the survivors in row order
+    keep = sorted(np.nonzero(grp == 2)[0][:4].tolist())
+    for row in keep:
+        ix.set_filter_bits(row, [3])
+    s, r = ix.query(q[None], 10, require_bits=[3], mode="scan")
+    assert r[0][:len(keep)].tolist() == keep and (r[0][len(keep):] == -1).all() and np.isneginf(s[0][len(keep):]).all()
+    ix.close()
+
+
 def test_zero_rows_and_zero_query(gpu):
     rng = np.random.default_rng(4)
     X = rng.standard_normal((100, 128)).astype(np.float32)

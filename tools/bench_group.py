@@ -25,10 +25,11 @@ def main():
     ap.add_argument("--devices", default="")
     ap.add_argument("--queries", type=int, default=500)
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--b-max", type=int, default=64)
     a = ap.parse_args()
     devs = [int(x) for x in a.devices.split(",")] if a.devices else list(range(torch.cuda.device_count()))
     G = len(devs)
-    gx = M.GroupIndex(a.dim, a.dtype, devices=devs, capacity=a.rows_per_gpu * G, b_max=64, k_max=32)
+    gx = M.GroupIndex(a.dim, a.dtype, devices=devs, capacity=a.rows_per_gpu * G, b_max=a.b_max, k_max=32)
     for s, sh in enumerate(gx.shards):
         dv = torch.device("cuda", sh.device)
         g = torch.Generator(device=dv)
@@ -52,7 +53,7 @@ def main():
         tl[i] = gx.last_timing_us()
     wall = time.perf_counter() - w0
     m = np.median(tl, axis=0)
-    print(json.dumps({"devices": devs, "rows_per_gpu": a.rows_per_gpu, "dim": a.dim, "dtype": a.dtype, "qps": a.queries / wall,
+    print(json.dumps({"devices": devs, "rows_per_gpu": a.rows_per_gpu, "dim": a.dim, "dtype": a.dtype, "b_max": a.b_max, "qps": a.queries / wall,
                       "latency_us": {"p50": float(np.percentile(lat, 50) * 1e6), "p99": float(np.percentile(lat, 99) * 1e6),
                                      "min": float(lat.min() * 1e6)},
                       "timeline_us_median": {"published": float(m[0]), "enqueued": float(m[1]), "flag_seen": float(m[2]),
