@@ -32,10 +32,12 @@ sweep) and 5 (2M x 768 all-pairs dedup, triangle split over the ranks).
 from __future__ import annotations
 
 import argparse
+import atexit
 import json
 import os
 import statistics
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -303,6 +305,13 @@ def check_planted(rows, scores, plants, want_scores, tol):
     return True, ""
 
 
+def unit_rows(torch, c0, n, dim, seed, device, g):
+    """synthetic unit-norm rows, generated on the device; the content depends only on (seed, global offset c0)"""
+    g.manual_seed(seed + c0)
+    x = torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
+    return torch.nn.functional.normalize(x, dim=1)
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -316,23 +325,49 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    cpu_group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        cpu_group = dist.new_group(backend="gloo")       # host-side barriers that keep the GPUs idle
     G = world
-    lo, hi = M.shard_bounds(args.rows, G, rank)
-    n_local = hi - lo
     tol = 2e-3 if args.dtype == "bf16" else 1e-5
     chunk = 1 << 19
+    k = args.k
+
+    # ---- parity plants (CPU only, before anything is timed) -------------------------------------
+    pq, plants = parity_plan(args.rows, args.dim)
+    NP = min(PARITY_QUERIES, queries_per_step(args, G))          # (a reduced --queries run checks fewer of them)
+    pq, plants = pq[:NP], plants[:NP]
+    want_scores = expected_scores(pq, plants, args.dtype)
+
+    # ---- one request at a time through the single-process group spanning all N GPUs (rank 0 only) -----------
+    # Measured FIRST, while rank 0 is the only process with a CUDA context on the box -- the deployment shape of that
+    # path is one server process owning all GPUs (backend/run.py:10-14).  The other torchrun ranks have not touched CUDA
+    # yet: they wait on a marker file, without torch.distributed (an NCCL rendezvous would create their contexts, and
+    # seven co-resident NCCL processes cost the group ~4 us per request: profiles/r02_group_latency.md).
+    per_query = None
+    marker = os.path.join(tempfile.gettempdir(), f"vs_bench_group_done_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}")
+    if args.group_queries > 0:
+        if rank == 0:
+            try:
+                per_query = group_per_query(args, M, torch, G, plants, pq, want_scores, tol)
+            except Exception as e:                    # noqa: BLE001 -- report, keep the headline
+                per_query = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            finally:
+                if world > 1:
+                    open(marker, "w").close()
+                    atexit.register(lambda: os.path.exists(marker) and os.unlink(marker))
+        elif world > 1:
+            t_wait = time.time()
+            while not os.path.exists(marker) and time.time() - t_wait < 900:
+                time.sleep(0.05)
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lo, hi = M.shard_bounds(args.rows, G, rank)
+    n_local = hi - lo
     gen = torch.Generator(device=dev)
 
     def corpus_chunk(c0, n, dim, seed=1234, device=dev, g=gen):
-        g.manual_seed(seed + c0)                  # chunk content depends only on its global offset
-        x = torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
-        return torch.nn.functional.normalize(x, dim=1)
+        return unit_rows(torch, c0, n, dim, seed, device, g)
 
     # ---- build the shard (synthetic unit-norm rows, generated on the device in chunks) --------
     ix = M.DeviceIndex(args.dim, args.dtype, device=local_rank, capacity=n_local, row_base=lo)
@@ -343,12 +378,7 @@ def run_ours(args):
     t_build = time.perf_counter() - t_build
     assert len(ix) == n_local
 
-    # ---- parity plants (before anything is timed) ----------------------------------------------
-    pq, plants = parity_plan(args.rows, args.dim)
-    NP = min(PARITY_QUERIES, queries_per_step(args, G))          # (a reduced --queries run checks fewer of them)
-    pq, plants = pq[:NP], plants[:NP]
-    want_scores = expected_scores(pq, plants, args.dtype)
-    for order in plants:
+    for order in plants:                                         # planted near-duplicates of the parity queries
         for g_row, v in order:
             if lo <= g_row < hi:
                 ix.set_row(g_row - lo, v)
@@ -358,7 +388,6 @@ def run_ours(args):
     q_host = torch.nn.functional.normalize(torch.randn((Q, args.dim), generator=gq), dim=1).pin_memory()
     q_host[:NP] = torch.from_numpy(pq)                      # the step's first queries are the parity queries
     q_dev = q_host.to(dev)
-    k = args.k
     cand_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
     cand_r = torch.empty((Q, k), dtype=torch.int64, device=dev)
     searcher, nccl_searcher, exchange = None, None, "none"
@@ -678,22 +707,6 @@ def run_ours(args):
     blocks_ms, (scan_ms, e2e_s, batched_ms, filter_ms, dedup_ms, xl_local, xl_rdv) = tl[:nb], tl[nb:]
     ix_closed = False
 
-    # ---- one request at a time through the single-process group spanning all N GPUs (rank 0 only) -----------
-    per_query = None
-    if args.group_queries > 0:
-        if G > 1:
-            ix.close()                               # free the shards; the other ranks idle on a HOST barrier
-            ix_closed = True
-            torch.cuda.synchronize()
-            dist.barrier(group=cpu_group)
-        if rank == 0:
-            try:
-                per_query = group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, tol)
-            except Exception as e:                    # noqa: BLE001 -- report, keep the headline
-                per_query = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-        if G > 1:
-            dist.barrier(group=cpu_group)
-
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
         elapsed_ms = statistics.median(blocks_ms)
@@ -786,7 +799,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, tol):
+def group_per_query(args, M, torch, G, plants, pq, want_scores, tol):
     """rank 0 only: build the corpus again as ONE single-process collection over all G GPUs and answer one
     request at a time through vs_group_query_host (what a uvicorn worker would call)."""
     n = args.rows
@@ -799,7 +812,7 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
         n_s = (n - s + G - 1) // G
         with torch.cuda.device(dv):
             for c0 in range(0, n_s, chunk):
-                sh.add(corpus_chunk(c0 + s * 7919, min(chunk, n_s - c0), args.dim, seed=4321, device=dv, g=g))
+                sh.add(unit_rows(torch, c0 + s * 7919, min(chunk, n_s - c0), args.dim, 4321, dv, g))
             torch.cuda.synchronize()
     assert len(gx) == n
     for order in plants:
@@ -833,7 +846,8 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
                           "min": float(lat.min() * 1e6)},
            "path": f"GroupIndex.query -> vs_group_query_host: ONE process, {G} GPU(s), one request at a time; query through a pinned "
                    "host-mapped area, one fused scan launch per GPU (exchange over NVLink inside the kernel), result + flag "
-                   "written to host-mapped memory by the kernel, polled by the caller (no stream synchronise)",
+                   "written to host-mapped memory by the kernel, polled by the caller (no stream synchronise); measured before "
+                   "the other torchrun ranks create their CUDA contexts (a server process owns the GPUs alone)",
            "timeline_us_median": {"query_published": float(tlm[0]), "all_launches_enqueued": float(tlm[1]),
                                   "completion_flag_seen": float(tlm[2]), "result_copied": float(tlm[3]),
                                   "python_and_ctypes": float(np.median(lat) * 1e6 - tlm[3])},
@@ -857,6 +871,9 @@ def group_per_query(args, M, torch, G, corpus_chunk, plants, pq, want_scores, to
         except Exception as e:                        # noqa: BLE001 -- keep the per-query numbers
             out["batched_multimodal_host"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     gx.close()
+    for d in range(G):                                # give the generator's scratch back: the ranks build their shards next
+        with torch.cuda.device(d):
+            torch.cuda.empty_cache()
     return out
 
 
