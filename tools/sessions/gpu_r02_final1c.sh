@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 FINAL 1-GPU session, part 2 (part 1 = tools/gpu_r02_final1b.sh: 113 gpu tests passed, smoke ok plain and under ncu;
+# round-2 FINAL 1-GPU session, part 2 (part 1 = tools/sessions/gpu_r02_final1b.sh: 113 gpu tests passed, smoke ok plain and under ncu;
 # its outputs exceeded the 64 MiB return limit): bench N=1, launch list of the bench command, one --set full capture of the
 # scan, and single-metric captures WITHOUT ncu's cache flush / replay (dram bytes of back-to-back scans)
 set -u
