@@ -243,7 +243,10 @@ int vs_exchange_collect_dev(vs_index_t* ix, int B, int k, float* out_scores_dev,
  *      memory, which the calling thread polls -- no stream synchronise, no result copy, no torchrun.
  *      B > 64 / the tcgen05 path / k > k_max (gathered onto GPU 0 over NVLink and merged there) use the
  *      same entry point.  Ingest and maintenance go through the shards: vs_group_shard(g, s) returns the
- *      vs_index_t of shard s (row map (s, n_dev) already set).  devices == NULL means 0..n_dev-1. */
+ *      vs_index_t of shard s (row map (s, n_dev) already set).  devices == NULL means 0..n_dev-1.
+ *      Errors: a peer that never pushes makes the kernels give up after ~3 s (VS_ERR_EXCHANGE, results empty); a
+ *      completion flag that never arrives (device fault) ends the poll after 30 s with VS_ERR_CUDA.  Both re-align the
+ *      shards' exchange epochs so that the next request starts clean. */
 typedef struct vs_group vs_group_t;
 int vs_group_create(int n_dev, const int* devices, int dim, int dtype, int64_t capacity_rows_total, int b_max,
                     int k_max, vs_group_t** out);

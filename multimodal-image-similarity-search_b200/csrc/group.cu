@@ -36,6 +36,8 @@ struct Request {
   uint64_t bits[kMaskWords] = {0, 0, 0, 0};
 };
 
+constexpr double kFlagTimeoutUs = 30e6;   // see run_request
+
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
   __builtin_ia32_pause();
@@ -257,9 +259,19 @@ int run_request(vs_group* gr, const void* in, size_t in_bytes, int B, int k, con
     return rc;
   }
   // shard 0's result: flags in host-mapped memory, raised by the kernel itself on the fused path
+  // (bounded: a kernel that died of an asynchronous CUDA error never raises its flag, and a server thread must not
+  // spin forever on it.  The longest legitimate fused request -- 64 scans of a 150M-row shard -- takes ~1.5 s.)
   volatile unsigned int* done = gr->h_done;
-  for (int b = 0; b < B; ++b)
-    while (done[b] != s) cpu_relax();
+  for (int b = 0; b < B; ++b) {
+    for (unsigned spins = 1; done[b] != s; ++spins) {
+      cpu_relax();
+      if ((spins & 0xFFFFFu) == 0 && since() > kFlagTimeoutUs) {
+        resync(gr);
+        return fail(VS_ERR_CUDA, "no completion flag for query %d of the request within %.0f s (device fault?)", b,
+                    kFlagTimeoutUs / 1e6);
+      }
+    }
+  }
   std::atomic_thread_fence(std::memory_order_acquire);
   gr->t_done_us = since();
   memcpy(out_scores, gr->h_out_s, (size_t)B * k * 4);
