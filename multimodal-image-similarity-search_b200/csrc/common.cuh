@@ -294,6 +294,58 @@ struct WarpTopK {
     refresh_threshold(k - 1);
   }
 
+  // REPLACE this list by the top-k (k <= 16) of `nlists` <= NL sorted key lists in shared memory -- no serial rounds at
+  // all: a bitonic merge TREE held in registers.  A register slot holds two lists: lanes 0-15 list 2s in order, lanes
+  // 16-31 list 2s+1 reversed = one bitonic sequence; five butterfly compare-exchange stages (64-bit shuffles) sort it, its
+  // top 16 sit in lanes 0-15; two sorted slots are paired the same way (one shuffle reverses the second into lanes 16-31)
+  // until one is left.  NL = 8: 3 levels x 5 stages on 4 + 2 + 1 slots, ~370 instructions, ~0.4 us, against ~2.3 us for
+  // the k = 10 rounds of select_sorted_smem (profiles/r02_group_latency.md).  Empty slots (key 0) sort last by themselves.
+  template <int NL>
+  __device__ __forceinline__ void merge_sorted_bitonic(const uint64_t* keys, int nlists, int stride, int k, int lane) {
+    static_assert(M == 1 && (NL == 8 || NL == 16), "8 or 16 lists of at most 16 entries");
+    constexpr int NS = NL / 2;
+    constexpr int LEVELS = NL == 8 ? 3 : 4;
+    uint64_t v[NS];
+    const int half = lane >> 4;
+    const int e = half ? 31 - lane : lane;   // entry of the list this lane holds (0..15)
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) {
+      const int li = 2 * sl + half;
+      v[sl] = (li < nlists && e < k) ? keys[(size_t)li * stride + e] : 0ull;
+    }
+#pragma unroll
+    for (int lvl = 0; lvl < LEVELS; ++lvl) {
+      const int width = NS >> lvl;           // live slots on this level (compile-time after unrolling)
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const bool up = (lane & d) == 0;     // this lane keeps the larger key of the pair
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+          if (sl < width) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, v[sl], d);
+            // keys are unique except for the empty key 0, where exchanging is a no-op: take the partner's key iff
+            // (it is larger) == (this lane keeps the larger one)
+            if ((other > v[sl]) == up) v[sl] = other;
+          }
+        }
+      }
+      if (width > 1) {
+#pragma unroll
+        for (int t = 0; t < NS / 2; ++t) {
+          if (t < width / 2) {
+            const uint64_t second = __shfl_sync(0xffffffffu, v[2 * t + 1], 31 - lane);   // its top 16, reversed, for lanes 16-31
+            v[t] = half ? second : v[2 * t];
+          }
+        }
+      }
+    }
+    const uint64_t w = lane < k ? v[0] : 0ull;
+    const uint32_t whi = (uint32_t)(w >> 32);
+    s[0] = whi == 0u ? VS_NEG_INF : key_score(whi);
+    r[0] = whi == 0u ? kEmptyRow : ~(uint32_t)w;
+    refresh_threshold(k - 1);
+  }
+
   // merge `nlists` sorted lists of k entries each (list i at src + i*stride) into this list.
   // Lane-parallel prefilter against the threshold, then serial insertion of the survivors.
   __device__ __forceinline__ void merge_from(const volatile float* src_s, const volatile uint32_t* src_r,

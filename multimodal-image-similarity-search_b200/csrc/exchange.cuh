@@ -115,7 +115,9 @@ __device__ __forceinline__ void xchg_wait_merge(const XchgParams& x, WarpTopK<M>
       __syncwarp();
       stage_lists_as_keys(ls, lr, x.G, (size_t)x.Bmax * x.kmax, k, sm_keys, lane);
       __syncwarp();
-      top.select_sorted_smem(sm_keys, x.G, k, k, lane);
+      static_assert(kMaxPeers <= 8, "the merge tree below takes at most 8 lists");
+      if (k <= 16) top.template merge_sorted_bitonic<8>(sm_keys, x.G, k, k, lane);
+      else top.select_sorted_smem(sm_keys, x.G, k, k, lane);
       return;
     }
   }

@@ -17,9 +17,10 @@
 //     up for rows that would enter the list -- zero extra traffic;
 //   * the per-warp lists are merged per CTA, written to a small global buffer, and the last
 //     CTA to finish (ticket) merges all CTA lists and writes the final [k] result: no second
-//     kernel, no score materialisation.  For k <= 32 every merge on this tail is a cursor selection
-//     over sorted lists of packed 64-bit keys in shared memory (WarpTopK::select_sorted_smem): the
-//     tail is pure latency for an isolated request (tools/scan_stamps.py, profiles/r02_group_latency.md).
+//     kernel, no score materialisation.  For k <= 32 the lists on this tail are sorted runs of packed
+//     64-bit keys in shared memory, merged by a register-held bitonic merge tree (8/16 lists, k <= 16:
+//     WarpTopK::merge_sorted_bitonic) or by cursor selection (WarpTopK::select_sorted_smem): the tail is
+//     pure latency for an isolated request (tools/scan_stamps.py, profiles/r02_group_latency.md).
 // Algorithmic HBM bytes per query = n_rows * (pitch + 4).
 #include <atomic>
 #include <cstdlib>
@@ -362,7 +363,8 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   if (!p.early_wait) pdl_wait();   // previous grid fully done: its partial lists / tickets / result rows are no longer in use
 
   // ---- per-CTA merge of the 8 warp lists ---------------------------------------------------
-  // k <= 32 (ML == 1): lists travel through shared memory as packed 64-bit keys and are merged by cursor selection
+  // k <= 32 (ML == 1): lists travel through shared memory as packed 64-bit keys; the W warp lists are merged by a
+  // register-held bitonic merge tree (k <= 16, WarpTopK::merge_sorted_bitonic) or by cursor selection
   // (WarpTopK::select_sorted_smem); the candidate area [W][32] x (f32 + u32) is exactly [W][32] keys.
   uint64_t* cand_k = reinterpret_cast<uint64_t*>(cand_s);
   if (warp < kConsumerWarps) {
@@ -373,8 +375,12 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   const size_t pbase = ((size_t)qi * gridDim.x + blockIdx.x) * k;
   if (warp == 0) {
     // all warps' lists (this warp's own is list 0)
-    if constexpr (ML == 1) top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
-    else top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
+    if constexpr (ML == 1) {
+      if (k <= 16) top.template merge_sorted_bitonic<kConsumerWarps>(cand_k, kConsumerWarps, 32, k, lane);
+      else top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
+    } else {
+      top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
+    }
     if (gridDim.x == 1) {
       emit_result<ML>(p, top, qi, k, lane, cand_k, kConsumerWarps * 32 * ML);   // single CTA: this is already the shard's answer
     } else {
@@ -431,8 +437,12 @@ __global__ void __launch_bounds__((W + 1) * 32, (M == 4 && W == 16) ? 1 : 2) sca
   }
   __syncthreads();
   if (warp == 0) {
-    if constexpr (ML == 1) top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
-    else top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
+    if constexpr (ML == 1) {
+      if (k <= 16) top.template merge_sorted_bitonic<kConsumerWarps>(cand_k, kConsumerWarps, 32, k, lane);
+      else top.select_sorted_smem(cand_k, kConsumerWarps, 32, k, lane);
+    } else {
+      top.select_from(cand_s, cand_r, kConsumerWarps, 32 * ML, k, lane);
+    }
     if (lane == 0) p.tickets[qi] = 0;  // ready for the next launch
     if (lane == 0) VS_STAMP_MAX(6);    // shard's top-k selected
     emit_result<ML>(p, top, qi, k, lane, cand_k, kConsumerWarps * 32 * ML);
