@@ -343,9 +343,14 @@ def run_ours(args):
     # yet: they wait on a marker file, without torch.distributed (an NCCL rendezvous would create their contexts, and
     # seven co-resident NCCL processes cost the group ~4 us per request: profiles/r02_group_latency.md).
     per_query = None
-    marker = os.path.join(tempfile.gettempdir(), f"vs_bench_group_done_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}")
+    # (keyed by the rendezvous port: every rank of one launch agrees on it whatever spawned them.  A stale file of a killed
+    # earlier run only makes the other ranks skip the wait, i.e. fall back to measuring with their contexts present.)
+    marker = os.path.join(tempfile.gettempdir(), "vs_bench_group_done_%s_%s" % (
+        os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "none")))
     if args.group_queries > 0:
         if rank == 0:
+            if world > 1 and os.path.exists(marker):
+                os.unlink(marker)
             try:
                 per_query = group_per_query(args, M, torch, G, plants, pq, want_scores, tol)
             except Exception as e:                    # noqa: BLE001 -- report, keep the headline
@@ -356,7 +361,7 @@ def run_ours(args):
                     atexit.register(lambda: os.path.exists(marker) and os.unlink(marker))
         elif world > 1:
             t_wait = time.time()
-            while not os.path.exists(marker) and time.time() - t_wait < 900:
+            while not os.path.exists(marker) and time.time() - t_wait < 300:
                 time.sleep(0.05)
 
     torch.cuda.set_device(local_rank)
